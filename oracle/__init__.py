@@ -1,0 +1,24 @@
+"""
+CPU oracle for the TASOC prepare-stage sky-background hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``photometry_b200`` may import this
+package; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` do.
+
+PARITY UNPINNED: the reference (``/root/reference``, pure Python) delegates the
+arithmetic of this path to photutils 1.3.0, astropy 5.1.0, statsmodels 0.13.2
+and Bottleneck 1.3.5, none of which is importable in the build container, and
+the reference's own tests hold no numerical golden vectors for the path beyond
+four trivial known answers.  This package restates those
+upstream algorithms in numpy + the real scipy; the four known answers are
+checked in ``tests/test_oracle_kat.py``.
+"""
+from .backgrounds_oracle import (  # noqa: F401
+	FFIImageLite, fit_background, pixel_manual_exclude, move_median_central,
+	reduce_mode, kde_density, sigma_clip_bounds, sextractor_background, Background2DOracle,
+	radial_geometry, XYCEN,
+)
+from .prepare_oracle import (  # noqa: F401
+	time_smooth_backgrounds, sumimage_accumulate, prepare_stack,
+	TESS_DEFAULT_BITMASK, PIXEL_NOT_USED_FOR_BACKGROUND, PIXEL_MANUAL_EXCLUDE,
+)
