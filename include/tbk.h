@@ -1,0 +1,147 @@
+/*
+ * tbk.h -- C ABI of the B200-native TASOC sky-background hot path ("tbk" = TESS background kernels).
+ *
+ * The reference (tasoc/photometry, pure Python) has no FFI for this path; its boundary is the
+ * Python call ``photometry.backgrounds.fit_background(image, ...) -> (bkg, mask)``
+ * (photometry/backgrounds.py:52-53,211) mapped over a process pool by
+ * ``photometry.prepare.prepare_photometry`` (photometry/prepare.py:278-291), followed by the
+ * time-smoothing loop (prepare.py:309-338) and the sumimage loop (prepare.py:347-470).
+ * Each entry point below names the reference lines it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions: every function returns 0 on success or a negative tbk_status; tbk_last_error()
+ * returns a thread-local message.  No exceptions, no torch types.  All image pointers are DEVICE
+ * pointers owned by the caller; every call is asynchronous on the given CUDA stream
+ * (``stream`` is a ``cudaStream_t`` passed as ``void*``; NULL = default stream).
+ */
+#ifndef TBK_H
+#define TBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBK_VERSION 1
+#define TBK_TILE 64           /* Background2D box size, backgrounds.py:200 */
+#define TBK_MAX_ROUNDS 8      /* upper limit for bkgiters */
+#define TBK_MAX_RINGS 256     /* upper limit for the number of radial rings */
+
+typedef enum {
+	TBK_OK = 0,
+	TBK_ERR_INVALID = -1,     /* bad argument (reference: ValueError) */
+	TBK_ERR_CUDA = -2,        /* CUDA runtime error */
+	TBK_ERR_NOMEM = -3
+} tbk_status;
+
+/* Per-FFI header scalars that drive the manual excludes (pixel_flags.py:34-56) and the sumimage
+ * gate (prepare.py:396-405,450). */
+typedef struct {
+	int32_t cadenceno;        /* FFIINDEX; INT32_MAX when absent (reference default: inf) */
+	int32_t dquality;         /* DQUALITY */
+	int32_t backapp;          /* BACKAPP: background already subtracted (prepare.py:419) */
+	int32_t reserved;
+	double  tstart;           /* TSTART */
+	double  tstop;            /* TSTOP */
+} tbk_ffi_meta;
+
+/* Per-FFI diagnostics written by tbk_fit_batch (device memory, caller-owned). */
+typedef struct {
+	int32_t all_masked;                   /* backgrounds.py:101-102 early-out: bkg = NaN */
+	int32_t no_good_mesh;                 /* photutils would raise ValueError: bkg = NaN */
+	int32_t n_valid;                      /* number of unmasked pixels */
+	int32_t rounds;                       /* rounds actually run */
+	int32_t n_excluded[TBK_MAX_ROUNDS];   /* meshes filled by IDW per round */
+	int32_t n_ring_valid[TBK_MAX_ROUNDS]; /* finite ring values after smoothing per round */
+	int32_t radial_ok[TBK_MAX_ROUNDS];    /* 1 when the spline was built (backgrounds.py:188-191) */
+	double  zeropoint[TBK_MAX_ROUNDS];    /* backgrounds.py:171 */
+} tbk_ffi_status;
+
+typedef struct tbk_plan tbk_plan;
+
+/*
+ * Plan = everything static for one (image shape, camera, ccd, parameter set): ring membership
+ * tables (backgrounds.py:145-154), per-tile geometry, interpolation weights.
+ *   H, W            image shape, multiples of TBK_TILE
+ *   is_tess         0: ndarray input semantics (no radial component, one round; backgrounds.py:155-157)
+ *   camera, ccd     1..4 when is_tess (unknown pair -> TBK_ERR_INVALID, backgrounds.py:139-140)
+ *   xycen_override  NULL, or {x, y} replacing the camera-centre table (test hook)
+ *   other args      the keyword arguments of fit_background (backgrounds.py:52-53)
+ */
+int tbk_plan_create(tbk_plan** plan, int H, int W, int is_tess, int camera, int ccd,
+	double flux_cutoff, int bkgiters, double radial_cutoff, double radial_pixel_step,
+	int radial_smooth, const double* xycen_override, int device);
+int tbk_plan_destroy(tbk_plan* plan);
+
+/* Number of rings / ring pixels of a plan (0 when the radial component is off). */
+int tbk_plan_num_rings(const tbk_plan* plan);
+
+/* Bytes of device scratch tbk_fit_batch needs for a batch of B FFIs. */
+size_t tbk_workspace_bytes(const tbk_plan* plan, int B);
+
+/*
+ * fit_background over a device-resident batch (backgrounds.py:86-211 per FFI; the pool loop of
+ * prepare.py:291).
+ *   cube        const float [B, H, W]   science pixels (FFIImage.data, io.py:47)
+ *   meta        const tbk_ffi_meta [B]  (device)
+ *   extra_mask  const uint8 [B, H, W] or NULL; non-zero = masked (star-mask extension, OR-ed at
+ *               the point of backgrounds.py:90)
+ *   bkg_out     float [B, H, W]         img_bkg_radial + img_bkg_square, rounded to float32 (the
+ *                                       reference casts to float32 at prepare.py:327-330)
+ *   mask_out    uint8 [B, H, W]         1 = pixel not used (the returned ``mask``; stored as
+ *                                       PixelQualityFlags.NotUsedForBackground, prepare.py:299)
+ *   status      tbk_ffi_status [B]      (device) or NULL
+ *   workspace   >= tbk_workspace_bytes(plan, B) bytes (device)
+ */
+int tbk_fit_batch(tbk_plan* plan, const float* cube, int B, const tbk_ffi_meta* meta,
+	const uint8_t* extra_mask, float* bkg_out, uint8_t* mask_out, tbk_ffi_status* status,
+	void* workspace, void* stream);
+
+/*
+ * Background time smoothing (prepare.py:317-335): out[k] = float32 nan-mean of
+ * bkg[max(k-w,0) .. min(k+w, N-1)] accumulated in index order.  The local shard holds cadences
+ * [0, n); halo_lo / halo_hi are the n_lo / n_hi (<= w) neighbouring frames owned by the previous /
+ * next shard (NULL / 0 at the ends of the sector).
+ */
+int tbk_time_smooth(tbk_plan* plan, const float* bkg, int n, int w,
+	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi,
+	float* bkg_smooth, void* stream);
+
+/*
+ * Final per-image loop (prepare.py:408-456) fused over the cadence axis:
+ *   flags[k]  |= ManualExclude where pixel_manual_exclude (prepare.py:408-410)
+ *   flux[k]    = cube[k] - bkg_smooth[k] (unless backapp), NaN where ManualExclude
+ *   if (dquality & 4335) == 0: nimg += isfinite(flux); sum += nan->0(flux)   (prepare.py:450-453)
+ *   used      += (flags & NotUsedForBackground) == 0                          (prepare.py:456)
+ * flux_out may be NULL.  sum / nimg / used are accumulated into (caller zeroes them first).
+ */
+int tbk_sum_accumulate(tbk_plan* plan, const float* cube, const float* bkg_smooth,
+	uint8_t* flags, const tbk_ffi_meta* meta, int n, float* flux_out,
+	double* sum, int32_t* nimg, int32_t* used, void* stream);
+
+/* prepare.py:459,468: sumimage = sum / nimg (0/0 -> NaN); pixels_used = used / numfiles > threshold. */
+int tbk_sum_finalize(tbk_plan* plan, const double* sum, const int32_t* nimg, const int32_t* used,
+	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, void* stream);
+
+/*
+ * Diagnostics of the most recent tbk_fit_batch on this plan (valid after the stream has been
+ * synchronised).  Copies, for FFI ``b`` and round ``round``: the ring values after smoothing
+ * (s2[nrings]), and the filtered low-resolution mesh (mesh[(H/64)*(W/64)]).  Either output may be NULL.
+ */
+int tbk_debug_fetch(tbk_plan* plan, const void* workspace, int B, int b, int round,
+	double* s2, double* mesh);
+
+/* Byte offsets of the workspace sections for a batch of B (diagnostics / tests):
+ * offsets[0..7] = ctl, tile_base, tile_nf, coef, mesh_hist, s2_raw, s2_hist, ring_v;
+ * sizes[0..2] = sizeof(FfiCtl), sizeof(TileStat), number of non-flat tiles. */
+int tbk_workspace_layout(const tbk_plan* plan, int B, size_t* offsets, size_t* sizes);
+
+const char* tbk_last_error(void);
+int tbk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBK_H */

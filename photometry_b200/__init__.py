@@ -1,0 +1,11 @@
+"""
+photometry_b200 -- B200-native (sm_100a) implementation of the TASOC prepare-stage sky-background hot
+path: ``photometry.backgrounds.fit_background`` over a CCD's FFI stack, background time smoothing and
+the sumimage accumulation.  Host side: Python + a C-ABI CUDA library (include/tbk.h).
+"""
+from .backgrounds import fit_background, BackgroundFitter, make_meta, meta_from_headers  # noqa: F401
+from .io import FFIImage  # noqa: F401
+from .quality import TESSQualityFlags, PixelQualityFlags  # noqa: F401
+from .prepare import prepare_stack, SectorResult  # noqa: F401
+
+__version__ = '0.1.0'

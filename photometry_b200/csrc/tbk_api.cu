@@ -1,0 +1,308 @@
+// tbk_api.cu -- C ABI (include/tbk.h): plan construction (static geometry tables) and entry points.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "tbk_common.cuh"
+#include "tbk_internal.h"
+
+static thread_local char g_err[512] = "";
+
+void tbk_set_error(const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char* tbk_last_error(void) { return g_err; }
+extern "C" int tbk_version(void) { return TBK_VERSION; }
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+	tbk_set_error("%s: %s", #x, cudaGetErrorString(e_)); return TBK_ERR_CUDA; } } while (0)
+
+struct tbk_plan {
+	PlanDev dev;
+	int device;
+	std::vector<void*> allocs;
+	int* zero_flags;
+	int zero_cap;
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv;
+};
+
+// photometry/backgrounds.py:121-138
+static const double XYCEN[4][4][2] = {
+	{{2158.222313, 2099.523364}, {-5.653058, 2098.018608}, {2141.511437, 2099.868226}, {-22.406442, 2100.116443}},
+	{{2148.588316, 2094.033024}, {-16.806140, 2095.810070}, {2151.351646, 2105.747100}, {-13.118570, 2105.982211}},
+	{{2152.175481, 2092.337442}, {-10.494413, 2093.108135}, {2145.029218, 2107.883573}, {-17.374782, 2105.296746}},
+	{{2149.259760, 2091.433315}, {-12.906931, 2093.350054}, {2148.906766, 2110.730620}, {-14.629676, 2111.341670}},
+};
+
+// volatile stores keep the host compiler from contracting a*b+c into an FMA: the ring membership
+// must match numpy's sqrt((xx - xc)**2 + (yy - yc)**2) bit for bit.
+static double host_radius(double xc, double yc, int y, int x)
+{
+	volatile double dx = (double)(x + 44) - xc;
+	volatile double dy = (double)y - yc;
+	volatile double a = dx * dx;
+	volatile double b = dy * dy;
+	volatile double s = a + b;
+	return std::sqrt(s);
+}
+static double host_edge(double cutoff, double step, int i)
+{
+	volatile double t = (double)i * step;
+	volatile double e = cutoff + t;
+	return e;
+}
+
+template <typename T>
+static int upload(tbk_plan* p, const std::vector<T>& v, const T** out)
+{
+	void* d = nullptr;
+	size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+	CUDA_TRY(cudaMalloc(&d, bytes));
+	p->allocs.push_back(d);
+	if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	*out = (const T*)d;
+	return TBK_OK;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void layout(tbk_plan* p, int B, size_t* total)
+{
+	const PlanDev& P = p->dev;
+	size_t o = 0;
+	p->off_ctl = o;    o = align_up(o + sizeof(FfiCtl) * (size_t)B);
+	p->off_base = o;   o = align_up(o + sizeof(TileStat) * (size_t)B * P.ntiles);
+	p->off_nf = o;     o = align_up(o + sizeof(TileStat) * (size_t)B * std::max(P.n_nonflat, 1));
+	p->off_coef = o;   o = align_up(o + sizeof(double) * (size_t)B * P.ntiles);
+	p->off_mesh = o;   o = align_up(o + sizeof(double) * (size_t)B * P.bkgiters * P.ntiles);
+	p->off_s2raw = o;  o = align_up(o + sizeof(double) * (size_t)B * std::max(P.nrings, 1));
+	p->off_s2hist = o; o = align_up(o + sizeof(double) * (size_t)B * P.bkgiters * std::max(P.nrings, 1));
+	p->off_ringv = o;  o = align_up(o + sizeof(double) * (size_t)B * std::max(P.nringpix, 1));
+	*total = o;
+}
+
+static Workspace carve(tbk_plan* p, void* base, int B)
+{
+	size_t total;
+	layout(p, B, &total);
+	char* b = (char*)base;
+	Workspace ws;
+	ws.ctl = (FfiCtl*)(b + p->off_ctl);
+	ws.tile_base = (TileStat*)(b + p->off_base);
+	ws.tile_nf = (TileStat*)(b + p->off_nf);
+	ws.coef = (double*)(b + p->off_coef);
+	ws.mesh_hist = (double*)(b + p->off_mesh);
+	ws.s2_raw = (double*)(b + p->off_s2raw);
+	ws.s2_hist = (double*)(b + p->off_s2hist);
+	ws.ring_v = (double*)(b + p->off_ringv);
+	return ws;
+}
+
+extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int camera, int ccd,
+	double flux_cutoff, int bkgiters, double radial_cutoff, double radial_pixel_step,
+	int radial_smooth, const double* xycen_override, int device)
+{
+	if (!out) { tbk_set_error("plan pointer is NULL"); return TBK_ERR_INVALID; }
+	*out = nullptr;
+	if (H <= 0 || W <= 0 || H % TBK_TILE || W % TBK_TILE) {
+		tbk_set_error("image shape (%d, %d) must be positive multiples of %d", H, W, TBK_TILE);
+		return TBK_ERR_INVALID;
+	}
+	if ((H / TBK_TILE) * (W / TBK_TILE) > 4096) { tbk_set_error("too many meshes (max 4096)"); return TBK_ERR_INVALID; }
+	if (bkgiters < 1 || bkgiters > TBK_MAX_ROUNDS) { tbk_set_error("bkgiters must be in 1..%d", TBK_MAX_ROUNDS); return TBK_ERR_INVALID; }
+	if (radial_smooth < 0 || radial_smooth > 63) { tbk_set_error("radial_smooth must be in 0..63"); return TBK_ERR_INVALID; }
+	double xc = 0, yc = 0;
+	if (is_tess) {
+		if (xycen_override) { xc = xycen_override[0]; yc = xycen_override[1]; }
+		else if (camera >= 1 && camera <= 4 && ccd >= 1 && ccd <= 4) { xc = XYCEN[camera - 1][ccd - 1][0]; yc = XYCEN[camera - 1][ccd - 1][1]; }
+		else { tbk_set_error("Invalid CAMERA or CCD in header: CAMERA=%d, CCD=%d", camera, ccd); return TBK_ERR_INVALID; }
+		if (!(radial_pixel_step > 0)) { tbk_set_error("radial_pixel_step must be positive"); return TBK_ERR_INVALID; }
+	}
+	CUDA_TRY(cudaSetDevice(device));
+	if (tbk_fit_configure() != TBK_OK) return TBK_ERR_CUDA;
+
+	tbk_plan* p = new tbk_plan();
+	p->device = device;
+	p->zero_flags = nullptr; p->zero_cap = 0;
+	PlanDev& P = p->dev;
+	memset(&P, 0, sizeof(P));
+	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;
+	P.is_tess = is_tess ? 1 : 0; P.use_radial = P.is_tess; P.camera = camera; P.ccd = ccd;
+	P.bkgiters = is_tess ? bkgiters : 1;  // backgrounds.py:155-157
+	P.radial_smooth = radial_smooth;
+	P.flux_cutoff = (float)flux_cutoff;
+	P.xc = xc; P.yc = yc; P.radial_cutoff = radial_cutoff; P.step = radial_pixel_step;
+
+	std::vector<int> ring_ptr(1, 0), ring_pix, nonflat, tile_slot(P.ntiles, -1);
+	if (P.use_radial) {
+		// backgrounds.py:145-154
+		std::vector<double> r((size_t)H * W);
+		double rmax = 0;
+		for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+			double v = host_radius(xc, yc, y, x);
+			r[(size_t)y * W + x] = v;
+			rmax = std::max(rmax, v);
+		}
+		const double radial_max = rmax + radial_pixel_step;
+		const long nedges = (long)std::ceil((radial_max - radial_cutoff) / radial_pixel_step);  // len(np.arange)
+		const int nrings = (int)nedges - 1;
+		if (nrings < 1) {
+			delete p;
+			tbk_set_error("radial_cutoff=%g leaves no radial bins inside the image (max r = %g)", radial_cutoff, rmax);
+			return TBK_ERR_INVALID;
+		}
+		if (nrings > TBK_MAX_RINGS) { delete p; tbk_set_error("too many radial rings (%d > %d)", nrings, TBK_MAX_RINGS); return TBK_ERR_INVALID; }
+		if (radial_smooth / 2 + 1 > nrings) { delete p; tbk_set_error("radial_smooth too wide for %d rings", nrings); return TBK_ERR_INVALID; }
+		P.nrings = nrings;
+		// ring id = searchsorted(bins, r, 'right') - 1, r == bins[-1] joins the last ring
+		std::vector<int> rid((size_t)H * W, -1);
+		std::vector<int> count(nrings, 0);
+		const double last_edge = host_edge(radial_cutoff, radial_pixel_step, nrings);
+		for (size_t i = 0; i < r.size(); ++i) {
+			const double v = r[i];
+			if (v < radial_cutoff) continue;
+			long k = (long)std::floor((v - radial_cutoff) / radial_pixel_step);
+			while (k + 1 <= nrings && host_edge(radial_cutoff, radial_pixel_step, (int)k + 1) <= v) ++k;
+			while (k > 0 && host_edge(radial_cutoff, radial_pixel_step, (int)k) > v) --k;
+			if (k >= nrings) { if (v == last_edge) k = nrings - 1; else continue; }
+			rid[i] = (int)k; ++count[k];
+		}
+		ring_ptr.assign(nrings + 1, 0);
+		for (int k = 0; k < nrings; ++k) ring_ptr[k + 1] = ring_ptr[k] + count[k];
+		ring_pix.resize(ring_ptr[nrings]);
+		std::vector<int> fill(ring_ptr.begin(), ring_ptr.end() - 1);
+		for (size_t i = 0; i < rid.size(); ++i) if (rid[i] >= 0) ring_pix[fill[rid[i]]++] = (int)i;
+		P.nringpix = (int)ring_pix.size();
+		// meshes that reach beyond the first ring centre see a non-constant radial component
+		const double c0 = host_edge(radial_cutoff, radial_pixel_step, 1) - radial_pixel_step / 2;
+		for (int t = 0; t < P.ntiles; ++t) {
+			const int ty = t / P.nx, tx = t % P.nx;
+			double m = 0;
+			const int ys[2] = {ty * TBK_TILE, ty * TBK_TILE + TBK_TILE - 1}, xs[2] = {tx * TBK_TILE, tx * TBK_TILE + TBK_TILE - 1};
+			for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) m = std::max(m, r[(size_t)ys[a] * W + xs[b]]);
+			if (m > c0) { tile_slot[t] = (int)nonflat.size(); nonflat.push_back(t); }
+		}
+		P.n_nonflat = (int)nonflat.size();
+	}
+	// cubic B-spline weights per sub-tile phase (scipy ni_interpolation.c, order 3):
+	// output o samples u = (o + 0.5)/64 - 0.5; x = u - floor(u)
+	std::vector<double> zw(64 * 4);
+	for (int o = 0; o < 64; ++o) {
+		const double u = ((double)o + 0.5) / 64.0 - 0.5;
+		const double x = u - std::floor(u);
+		const double y = x, z = 1.0 - x;
+		double w0 = z * z * z / 6.0;
+		double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+		double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+		double w3 = 1.0 - w0 - w1 - w2;
+		zw[o * 4 + 0] = w0; zw[o * 4 + 1] = w1; zw[o * 4 + 2] = w2; zw[o * 4 + 3] = w3;
+	}
+	std::vector<double2> tw(TBK_KDE_M / 2);
+	for (int k = 0; k < TBK_KDE_M / 2; ++k) {
+		const double ang = -2.0 * M_PI * (double)k / (double)TBK_KDE_M;
+		tw[k] = make_double2(std::cos(ang), std::sin(ang));
+	}
+	int rc;
+	if ((rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
+		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
+		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle))) {
+		tbk_plan_destroy(p);
+		return rc;
+	}
+	*out = p;
+	return TBK_OK;
+}
+
+extern "C" int tbk_plan_destroy(tbk_plan* p)
+{
+	if (!p) return TBK_OK;
+	cudaSetDevice(p->device);
+	for (void* d : p->allocs) cudaFree(d);
+	if (p->zero_flags) cudaFree(p->zero_flags);
+	delete p;
+	return TBK_OK;
+}
+
+extern "C" int tbk_plan_num_rings(const tbk_plan* p) { return p ? p->dev.nrings : 0; }
+
+extern "C" size_t tbk_workspace_bytes(const tbk_plan* p, int B)
+{
+	if (!p || B <= 0) return 0;
+	size_t total;
+	layout(const_cast<tbk_plan*>(p), B, &total);
+	return total;
+}
+
+extern "C" int tbk_fit_batch(tbk_plan* p, const float* cube, int B, const tbk_ffi_meta* meta,
+	const uint8_t* extra_mask, float* bkg_out, uint8_t* mask_out, tbk_ffi_status* status,
+	void* workspace, void* stream)
+{
+	if (!p || !cube || !bkg_out || !mask_out || !workspace || B <= 0) { tbk_set_error("tbk_fit_batch: NULL argument or B <= 0"); return TBK_ERR_INVALID; }
+	if (p->dev.is_tess && !meta) { tbk_set_error("tbk_fit_batch: meta is required for TESS plans"); return TBK_ERR_INVALID; }
+	if (((uintptr_t)cube | (uintptr_t)bkg_out) & 15 || ((uintptr_t)mask_out & 3) || ((uintptr_t)extra_mask & 3) || ((uintptr_t)workspace & 255)) {
+		tbk_set_error("tbk_fit_batch: misaligned pointer (cube/bkg 16 B, masks 4 B, workspace 256 B)");
+		return TBK_ERR_INVALID;
+	}
+	Workspace ws = carve(p, workspace, B);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_time_smooth(tbk_plan* p, const float* bkg, int n, int w,
+	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi, float* out, void* stream)
+{
+	if (!p || !bkg || !out || n <= 0 || w < 0) { tbk_set_error("tbk_time_smooth: bad argument"); return TBK_ERR_INVALID; }
+	if ((n_lo > 0 && !halo_lo) || (n_hi > 0 && !halo_hi) || n_lo < 0 || n_hi < 0) { tbk_set_error("tbk_time_smooth: bad halo"); return TBK_ERR_INVALID; }
+	return tbk_launch_time_smooth(p->dev.H, p->dev.W, bkg, n, w, halo_lo, n_lo, halo_hi, n_hi, out, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_sum_accumulate(tbk_plan* p, const float* cube, const float* bkg_smooth,
+	uint8_t* flags, const tbk_ffi_meta* meta, int n, float* flux_out,
+	double* sum, int32_t* nimg, int32_t* used, void* stream)
+{
+	if (!p || !cube || !bkg_smooth || !flags || !meta || !sum || !nimg || !used || n <= 0) { tbk_set_error("tbk_sum_accumulate: bad argument"); return TBK_ERR_INVALID; }
+	if (n > p->zero_cap) {
+		if (p->zero_flags) CUDA_TRY(cudaFree(p->zero_flags));
+		p->zero_flags = nullptr; p->zero_cap = 0;
+		CUDA_TRY(cudaMalloc((void**)&p->zero_flags, sizeof(int) * (size_t)n));
+		p->zero_cap = n;
+	}
+	return tbk_launch_sum_accumulate(p->dev, cube, bkg_smooth, flags, meta, n, flux_out, sum, nimg, used, p->zero_flags, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_sum_finalize(tbk_plan* p, const double* sum, const int32_t* nimg, const int32_t* used,
+	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, void* stream)
+{
+	if (!p || !sum || !nimg || !used || !sumimage || !pixels_used || numfiles <= 0) { tbk_set_error("tbk_sum_finalize: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_sum_finalize(p->dev.H, p->dev.W, sum, nimg, used, numfiles, threshold, sumimage, pixels_used, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_debug_fetch(tbk_plan* p, const void* workspace, int B, int b, int round, double* s2, double* mesh)
+{
+	if (!p || !workspace || b < 0 || b >= B || round < 0 || round >= p->dev.bkgiters) { tbk_set_error("tbk_debug_fetch: bad argument"); return TBK_ERR_INVALID; }
+	Workspace ws = carve(p, const_cast<void*>(workspace), B);
+	const PlanDev& P = p->dev;
+	if (s2 && P.nrings > 0)
+		CUDA_TRY(cudaMemcpy(s2, ws.s2_hist + ((size_t)b * P.bkgiters + round) * P.nrings, sizeof(double) * P.nrings, cudaMemcpyDeviceToHost));
+	if (mesh)
+		CUDA_TRY(cudaMemcpy(mesh, ws.mesh_hist + ((size_t)b * P.bkgiters + round) * P.ntiles, sizeof(double) * P.ntiles, cudaMemcpyDeviceToHost));
+	return TBK_OK;
+}
+
+extern "C" int tbk_workspace_layout(const tbk_plan* p, int B, size_t* offsets, size_t* sizes)
+{
+	if (!p || B <= 0 || !offsets || !sizes) { tbk_set_error("tbk_workspace_layout: bad argument"); return TBK_ERR_INVALID; }
+	size_t total;
+	tbk_plan* q = const_cast<tbk_plan*>(p);
+	layout(q, B, &total);
+	offsets[0] = q->off_ctl; offsets[1] = q->off_base; offsets[2] = q->off_nf; offsets[3] = q->off_coef;
+	offsets[4] = q->off_mesh; offsets[5] = q->off_s2raw; offsets[6] = q->off_s2hist; offsets[7] = q->off_ringv;
+	sizes[0] = sizeof(FfiCtl); sizes[1] = sizeof(TileStat); sizes[2] = (size_t)p->dev.n_nonflat;
+	return TBK_OK;
+}

@@ -1,0 +1,287 @@
+// tbk_common.cuh -- shared device structures and block-level primitives (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/tbk.h"
+
+#define TBK_NT 256            // threads per tile CTA
+#define TBK_VPT 16            // pixels per thread in a tile CTA (64*64 / 256)
+#define TBK_NBINS 1024        // histogram bins for exact selection
+#define TBK_CAND 256          // max candidates resolved by rank counting
+#define TBK_KDE_M 2048        // KDE grid (2**ceil(log2(2000)), statsmodels kdensityfft)
+#define TBK_NPIX_TILE (TBK_TILE * TBK_TILE)
+
+// ---------------------------------------------------------------------------------------------
+// Static per-plan description, passed by value to kernels.
+struct PlanDev {
+	int H, W, ny, nx, ntiles;
+	int is_tess, use_radial, camera, ccd;
+	int bkgiters, radial_smooth;
+	float flux_cutoff;          // compared in float32 like ``img0.data > flux_cutoff``
+	double xc, yc;              // camera centre (backgrounds.py:121-138)
+	double radial_cutoff, step; // ring edges: cutoff + i*step
+	int nrings;                 // len(bins) - 1
+	int nringpix;               // pixels with a ring id
+	int n_nonflat;              // tiles with max(r) > first ring centre
+	// device tables
+	const int* ring_ptr;        // [nrings + 1] CSR offsets into ring_pix
+	const int* ring_pix;        // [nringpix] linear pixel index y*W + x, row-major within a ring
+	const int* nonflat_tiles;   // [n_nonflat] tile ids
+	const int* tile_slot;       // [ntiles] index into nonflat list or -1 (flat tile)
+	const double* zoom_w;       // [64][4] cubic B-spline weights per sub-tile phase
+	const double2* twiddle;     // [TBK_KDE_M/2] exp(-2 pi i k / M)
+};
+
+// Sigma-clipped statistics of one mesh (values are about the tile's own data, before any shift).
+struct TileStat {
+	double mean, med, std;
+	int nfin;                   // pixels surviving mask + clip; nbad = 4096 - nfin
+	int pad;
+};
+
+// Per-FFI dynamic state.
+struct FfiCtl {
+	unsigned int min_bits;      // min over valid pixels of x (float bits, x >= 0)
+	int any_nonzero;            // some pixel != 0 (NaN counts), pixel_flags.py:54
+	int n_valid;
+	int mars, earth;            // manual excludes decided from the header scalars
+	int all_masked;
+	int no_good_mesh;
+	int radial_ok;              // current round: spline available
+	int npts;                   // spline knots
+	int mesh_const;             // ptp(mesh) == 0
+	unsigned long long min_key; // rounds >= 2: ordered key of min(x - sq)
+	double zp;                  // zeropoint of the current round
+	double c_flat;              // radial value for r <= x0 (10**y0 - zp), 0 when !radial_ok
+	double x0, xlast;           // spline abscissa range (ext=3 clamp)
+	double mesh_min, mesh_max;
+	double kx[TBK_MAX_RINGS];       // knot abscissae
+	double pp[TBK_MAX_RINGS][4];    // piecewise cubic: y = pp0 + s*(pp1 + s*(pp2 + s*pp3)), s = t - kx[i]
+	short seg_of_ring[TBK_MAX_RINGS]; // ring-centre interval -> spline piece
+};
+
+// Workspace carve-up (all pointers into the caller's scratch buffer).
+struct Workspace {
+	FfiCtl* ctl;            // [B]
+	TileStat* tile_base;    // [B][ntiles]
+	TileStat* tile_nf;      // [B][n_nonflat]
+	double* coef;           // [B][ntiles] prefiltered cubic-spline coefficients of the current round
+	double* mesh_hist;      // [B][rounds][ntiles] filtered mesh per round (diagnostics)
+	double* s2_raw;         // [B][nrings] ring modes of the current round
+	double* s2_hist;        // [B][rounds][nrings] smoothed ring values per round (diagnostics)
+	double* ring_v;         // [B][nringpix] ring samples (NaN = masked)
+};
+
+// ---------------------------------------------------------------------------------------------
+// numeric helpers
+
+__device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ float nan_f() { return __int_as_float(0x7fc00000); }
+
+// r exactly as numpy computes sqrt((xx - xc)**2 + (yy - yc)**2): no FMA contraction.
+__device__ __forceinline__ double pixel_radius(const PlanDev& P, int y, int x)
+{
+	double dx = __dsub_rn((double)(x + 44), P.xc);
+	double dy = __dsub_rn((double)y, P.yc);
+	return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+// Centre of ring i: (bins[1:] - step/2)[i] with bins = arange(cutoff, ..., step)  (backgrounds.py:152-154).
+__device__ __forceinline__ double ring_center(const PlanDev& P, int i)
+{
+	return __dsub_rn(__dadd_rn(P.radial_cutoff, __dmul_rn((double)(i + 1), P.step)), P.step / 2);
+}
+
+// Order-preserving map double -> uint64 (for atomicMin on mixed-sign doubles).
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+	unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k)
+{
+	unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+	return __longlong_as_double((long long)b);
+}
+
+// Validity of a pixel: backgrounds.py:91-97 (finite, <= cutoff, >= 0, manual excludes, extra mask).
+__device__ __forceinline__ bool pixel_valid(float x, float cutoff)
+{
+	// NaN fails both comparisons; +inf fails x <= cutoff.
+	return (x >= 0.0f) && (x <= cutoff);
+}
+
+// Radial component at radius r for the current round (10**spline(clamp(r)) - zp), backgrounds.py:191.
+__device__ __forceinline__ double radial_value(const FfiCtl& c, const PlanDev& P, double r)
+{
+	if (!c.radial_ok) return 0.0;
+	if (r <= c.x0) return c.c_flat;
+	double t = fmin(r, c.xlast);
+	// ring centres are cutoff + step/2 + i*step; seg_of_ring maps the centre interval to the piece
+	int i = (int)floor((t - ring_center(P, 0)) / P.step);
+	i = max(0, min(i, P.nrings - 1));
+	int s = c.seg_of_ring[i];
+	// guard against rounding at interval ends
+	while (s + 1 < c.npts - 1 && t >= c.kx[s + 1]) ++s;
+	while (s > 0 && t < c.kx[s]) --s;
+	double u = t - c.kx[s];
+	double y = c.pp[s][0] + u * (c.pp[s][1] + u * (c.pp[s][2] + u * c.pp[s][3]));
+	return exp10(y) - c.zp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block reductions for TBK_NT (or any multiple of 32 up to 1024) threads.  Every thread returns the
+// same value (partials are combined in a fixed order, so results are deterministic).
+struct RedSmem {
+	double d[3][32];
+	int i[2][32];
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ int warp_sum(int v)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+	for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// sum of (int n, double a, double b)
+__device__ __forceinline__ void block_sum3(RedSmem& s, int& n, double& a, double& b)
+{
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	n = warp_sum(n); a = warp_sum(a); b = warp_sum(b);
+	__syncthreads();
+	if (lane == 0) { s.i[0][w] = n; s.d[0][w] = a; s.d[1][w] = b; }
+	__syncthreads();
+	n = 0; a = 0.0; b = 0.0;
+	for (int k = 0; k < nw; ++k) { n += s.i[0][k]; a += s.d[0][k]; b += s.d[1][k]; }
+}
+// (int sum, double min, double max)
+__device__ __forceinline__ void block_sum_min_max(RedSmem& s, int& n, double& mn, double& mx)
+{
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	n = warp_sum(n); mn = warp_min(mn); mx = warp_max(mx);
+	__syncthreads();
+	if (lane == 0) { s.i[0][w] = n; s.d[0][w] = mn; s.d[1][w] = mx; }
+	__syncthreads();
+	n = 0; mn = INFINITY; mx = -INFINITY;
+	for (int k = 0; k < nw; ++k) { n += s.i[0][k]; mn = fmin(mn, s.d[0][k]); mx = fmax(mx, s.d[1][k]); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact k-th smallest (0-based) of a distributed multiset by iterated histogram refinement.
+//
+// The caller supplies a functor ``each(f)`` that calls ``f(value_as_double)`` for every element this
+// thread owns (register arrays or a strided sweep over global memory).  ``a <= elements <= b`` must
+// hold.  Bins are a monotone non-decreasing function of the value, so after locating the bin that
+// holds rank k the search recurses into the exact [min, max] of that bin; a bin with at most
+// TBK_CAND members is resolved by rank counting.  Works for float32 data too (float -> double is exact).
+struct SelectSmem {
+	unsigned int hist[TBK_NBINS];
+	double cand[TBK_CAND];
+	unsigned int wsum[32];
+	int ncand;
+	int sel_bin, sel_excl, sel_cnt;
+	double result;
+};
+
+template <typename Each>
+__device__ double block_select(SelectSmem& sm, RedSmem& rs, Each each, int k, double a, double b)
+{
+	const int tid = threadIdx.x, nt = blockDim.x;
+	const int lane = tid & 31, w = tid >> 5, nw = (nt + 31) >> 5;
+	for (int level = 0; level < 64; ++level) {
+		if (!(a < b)) return a;
+		const double scale = (double)TBK_NBINS / (b - a);
+		for (int i = tid; i < TBK_NBINS; i += nt) sm.hist[i] = 0u;
+		if (tid == 0) sm.ncand = 0;
+		__syncthreads();
+		each([&](double v) {
+			if (v >= a && v <= b) {
+				int bin = min(TBK_NBINS - 1, (int)((v - a) * scale));
+				atomicAdd(&sm.hist[bin], 1u);
+			}
+		});
+		__syncthreads();
+		// exclusive scan over bins: thread t owns bins [t*per, (t+1)*per)
+		const int per = (TBK_NBINS + nt - 1) / nt;
+		unsigned int loc[8];
+		unsigned int tsum = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (j < per) {
+				int bi = tid * per + j;
+				loc[j] = (bi < TBK_NBINS) ? sm.hist[bi] : 0u;
+				tsum += loc[j];
+			}
+		}
+		unsigned int inc = tsum;
+		for (int o = 1; o < 32; o <<= 1) {
+			unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += t;
+		}
+		if (lane == 31) sm.wsum[w] = inc;
+		__syncthreads();
+		unsigned int base = 0;
+		for (int q = 0; q < w; ++q) base += sm.wsum[q];
+		unsigned int excl = base + inc - tsum;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (j < per) {
+				if ((unsigned)k >= excl && (unsigned)k < excl + loc[j]) {
+					sm.sel_bin = tid * per + j; sm.sel_excl = (int)excl; sm.sel_cnt = (int)loc[j];
+				}
+				excl += loc[j];
+			}
+		}
+		__syncthreads();
+		const int sbin = sm.sel_bin, sexcl = sm.sel_excl, scnt = sm.sel_cnt;
+		if (scnt <= TBK_CAND) {
+			each([&](double v) {
+				if (v >= a && v <= b) {
+					int bin = min(TBK_NBINS - 1, (int)((v - a) * scale));
+					if (bin == sbin) { int p = atomicAdd(&sm.ncand, 1); sm.cand[p] = v; }
+				}
+			});
+			__syncthreads();
+			const int kk = k - sexcl;
+			for (int j = tid; j < scnt; j += nt) {
+				const double cj = sm.cand[j];
+				int r = 0;
+				for (int i = 0; i < scnt; ++i) {
+					const double ci = sm.cand[i];
+					r += (ci < cj) || (ci == cj && i < j);
+				}
+				if (r == kk) sm.result = cj;
+			}
+			__syncthreads();
+			return sm.result;
+		}
+		// recurse into the tight range of the selected bin
+		int cnt = 0; double mn = INFINITY, mx = -INFINITY;
+		each([&](double v) {
+			if (v >= a && v <= b) {
+				int bin = min(TBK_NBINS - 1, (int)((v - a) * scale));
+				if (bin == sbin) { ++cnt; mn = fmin(mn, v); mx = fmax(mx, v); }
+			}
+		});
+		block_sum_min_max(rs, cnt, mn, mx);
+		k -= sexcl; a = mn; b = mx;
+		__syncthreads();
+	}
+	return a;
+}

@@ -1,0 +1,741 @@
+// tbk_fit.cu -- kernels of the batched fit_background path (photometry/backgrounds.py:86-211).
+#include "tbk_common.cuh"
+#include "tbk_tile.cuh"
+#include "tbk_zoom.cuh"
+#include "tbk_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// K_init: per-FFI control block; manual excludes from header scalars (pixel_flags.py:34-50).
+__global__ void k_init_ctl(PlanDev P, Workspace ws, const tbk_ffi_meta* __restrict__ meta, int B)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= B) return;
+	FfiCtl& c = ws.ctl[b];
+	c.min_bits = 0x7f800000u;
+	c.any_nonzero = 0;
+	c.n_valid = 0;
+	c.all_masked = 0;
+	c.no_good_mesh = 0;
+	c.radial_ok = 0;
+	c.npts = 0;
+	c.mesh_const = 0;
+	c.min_key = ~0ULL;
+	c.zp = 0.0; c.c_flat = 0.0; c.x0 = 0.0; c.xlast = 0.0;
+	c.mesh_min = 0.0; c.mesh_max = 0.0;
+	int mars = 0, earth = 0;
+	if (P.is_tess) {
+		const tbk_ffi_meta m = meta[b];
+		const double time = 0.5 * (m.tstart + m.tstop);
+		const int cad = m.cadenceno;
+		if (P.camera == 1 && P.ccd == 4 && (cad <= 4724 || m.tstart <= 1325.881282301840)) mars = 1;
+		else if (P.camera == 1 && ((cad >= 11354 && cad <= 11366) || (time >= 1464.0158778 && time <= 1464.265871))) earth = 1;
+	}
+	c.mars = mars; c.earth = earth;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_tile_base: mask build (backgrounds.py:91-97), per-FFI min / flags, and sigma-clipped statistics
+// of every mesh on the raw pixels.  Meshes that can see r > first ring centre ("non-flat") are
+// re-evaluated each round by k_tile_round instead.
+__global__ void __launch_bounds__(TBK_NT) k_tile_base(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
+{
+	__shared__ TileSmem sm;
+	__shared__ int s_flag;
+	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	FfiCtl& c = ws.ctl[b];
+	const size_t img = (size_t)b * P.H * P.W;
+	const int lcol = tile_lcol(tid);
+	const int gx = tx * TBK_TILE + lcol;
+	const bool mars_cols = c.mars && gx >= 1536;
+	const bool earth = c.earth;
+
+	float v[TBK_VPT];
+	unsigned valid = 0;
+	bool nonzero = false;
+	float4 raw[4];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int gy = ty * TBK_TILE + tile_lrow(tid, j);
+		raw[j] = __ldg(reinterpret_cast<const float4*>(cube + img + (size_t)gy * P.W + gx));
+	}
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int gy = ty * TBK_TILE + tile_lrow(tid, j);
+		const size_t off = img + (size_t)gy * P.W + gx;
+		const float x4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+		uchar4 ex = make_uchar4(0, 0, 0, 0);
+		if (extra) ex = __ldg(reinterpret_cast<const uchar4*>(extra + off));
+		const unsigned char e4[4] = {ex.x, ex.y, ex.z, ex.w};
+		unsigned char m4[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const float x = x4[q];
+			nonzero |= !(x == 0.0f);
+			const bool ok = pixel_valid(x, P.flux_cutoff) && !mars_cols && !earth && !e4[q];
+			v[4 * j + q] = x + 0.0f;  // -0.0 -> +0.0
+			valid |= (ok ? 1u : 0u) << (4 * j + q);
+			m4[q] = ok ? 0 : 1;
+		}
+		*reinterpret_cast<uchar4*>(mask_out + off) = make_uchar4(m4[0], m4[1], m4[2], m4[3]);
+	}
+
+	// per-FFI reductions: any pixel != 0, number of valid pixels, min of valid pixels
+	if (tid == 0) s_flag = 0;
+	__syncthreads();
+	if (nonzero) s_flag = 1;
+	int cnt = __popc(valid);
+	float mnf = INFINITY;
+#pragma unroll
+	for (int e = 0; e < TBK_VPT; ++e) if (valid >> e & 1u) mnf = fminf(mnf, v[e]);
+	double mn = mnf, mx = 0.0;
+	block_sum_min_max(sm.red, cnt, mn, mx);
+	if (tid == 0) {
+		if (s_flag && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+		if (cnt > 0) {
+			atomicAdd(&c.n_valid, cnt);
+			atomicMin(&c.min_bits, __float_as_uint((float)mn));
+		}
+	}
+
+	const bool nonflat = P.use_radial && P.tile_slot[tile] >= 0;
+	if (nonflat) return;
+	TileStat st = tile_sigma_clip<float>(v, valid, sm);
+	if (tid == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+}
+
+// K_post_base: all-zero rule (pixel_flags.py:54-56), all-masked early-out (backgrounds.py:101-102),
+// zeropoint of round 1 (backgrounds.py:171).
+__global__ void k_post_base(PlanDev P, Workspace ws, tbk_ffi_status* status, int B)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= B) return;
+	FfiCtl& c = ws.ctl[b];
+	if (P.is_tess && !c.any_nonzero) { c.all_masked = 1; c.n_valid = 0; }
+	if (c.n_valid == 0) c.all_masked = 1;
+	c.zp = 1.0 - (double)__uint_as_float(c.min_bits);
+	if (status) {
+		tbk_ffi_status& s = status[b];
+		s.all_masked = c.all_masked;
+		s.no_good_mesh = 0;
+		s.n_valid = c.n_valid;
+		s.rounds = 0;
+		for (int i = 0; i < TBK_MAX_ROUNDS; ++i) {
+			s.n_excluded[i] = 0; s.n_ring_valid[i] = 0; s.radial_ok[i] = 0; s.zeropoint[i] = 0.0;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_zp_min (rounds >= 2): min over valid pixels of x - img_bkg_square (backgrounds.py:165-171).
+__global__ void __launch_bounds__(TBK_NT) k_zp_min(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
+{
+	__shared__ ZoomTile z;
+	__shared__ RedSmem red;
+	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	zoom_tile_load(z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
+	__syncthreads();
+	const size_t img = (size_t)b * P.H * P.W;
+	const int lcol = tile_lcol(tid);
+	double mn = INFINITY, mx = 0.0; int cnt = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int lrow = tile_lrow(tid, j);
+		const size_t off = img + (size_t)(ty * TBK_TILE + lrow) * P.W + tx * TBK_TILE + lcol;
+		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
+		const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + off));
+		double sq[4];
+		zoom_eval4(z, P.zoom_w, lrow, lcol, sq);
+		if (!m.x) mn = fmin(mn, (double)x.x - zoom_clip(c, sq[0]));
+		if (!m.y) mn = fmin(mn, (double)x.y - zoom_clip(c, sq[1]));
+		if (!m.z) mn = fmin(mn, (double)x.z - zoom_clip(c, sq[2]));
+		if (!m.w) mn = fmin(mn, (double)x.w - zoom_clip(c, sq[3]));
+	}
+	block_sum_min_max(red, cnt, mn, mx);
+	if (tid == 0 && mn < INFINITY) atomicMin(&c.min_key, dkey(mn));
+}
+
+__global__ void k_set_zp(Workspace ws, int B)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= B) return;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	c.zp = 1.0 - dkey_inv(c.min_key);  // zeropoint = -min(pix) + 1.0
+	c.min_key = ~0ULL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_ring_gather: log-flux samples of every ring pixel (backgrounds.py:165-172).
+// round 0: float32 arithmetic with a correctly rounded float32 log10; later rounds float64.
+__global__ void k_ring_gather(PlanDev P, Workspace ws, const float* __restrict__ cube,
+	const uint8_t* __restrict__ mask, int round)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int b = blockIdx.y;
+	if (i >= P.nringpix) return;
+	const FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int pix = __ldg(P.ring_pix + i);
+	const size_t off = (size_t)b * P.H * P.W + pix;
+	double val = nan_d();
+	if (!__ldg(mask + off)) {
+		const float x = __ldg(cube + off);
+		if (round == 0) {
+			const float s = (x + 0.0f) + (float)c.zp;
+			val = (double)(float)log10((double)s);
+		} else {
+			const int y = pix / P.W, xx = pix % P.W;
+			const double sq = zoom_clip(c, zoom_eval_global(ws.coef + (size_t)b * P.ntiles, P.zoom_w, y, xx, P.ny, P.nx));
+			val = log10(((double)x - sq) + c.zp);
+		}
+	}
+	ws.ring_v[(size_t)b * P.nringpix + i] = val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_ring_kde: mode of a Gaussian FFT-KDE per ring (backgrounds.py:21-33 + statsmodels 0.13.2
+// KDEUnivariate.fit(gridsize=2000); see oracle/backgrounds_oracle.py:kde_density).
+#define TBK_KDE_NT 512
+struct KdeSmem {
+	double2 x[TBK_KDE_M];
+	SelectSmem sel;
+	RedSmem red;
+	double bestv[32];
+	int besti[32];
+};
+
+__device__ __forceinline__ void kde_fft(double2* x, const double2* __restrict__ tw, bool inverse)
+{
+	// iterative radix-2 DIT on bit-reversed input; M = 2048, blockDim = 512
+	const int tid = threadIdx.x, nt = blockDim.x;
+	for (int s = 1; s <= 11; ++s) {
+		const int half = 1 << (s - 1);
+		const int tstep = TBK_KDE_M >> s;
+		for (int idx = tid; idx < TBK_KDE_M / 2; idx += nt) {
+			const int j = idx & (half - 1);
+			const int k = ((idx >> (s - 1)) << s) + j;
+			double2 w = __ldg(tw + j * tstep);
+			if (inverse) w.y = -w.y;
+			const double2 u = x[k], t = x[k + half];
+			const double2 wt = make_double2(w.x * t.x - w.y * t.y, w.x * t.y + w.y * t.x);
+			x[k] = make_double2(u.x + wt.x, u.y + wt.y);
+			x[k + half] = make_double2(u.x - wt.x, u.y - wt.y);
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	KdeSmem& sm = *reinterpret_cast<KdeSmem*>(smraw);
+	const int ring = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+	const FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int lo = P.ring_ptr[ring], hi = P.ring_ptr[ring + 1];
+	const double* __restrict__ v = ws.ring_v + (size_t)b * P.nringpix;
+	double* out = ws.s2_raw + (size_t)b * P.nrings + ring;
+
+	auto each = [&](auto f) {
+		for (int i = lo + tid; i < hi; i += nt) { const double d = v[i]; if (d == d) f(d); }
+	};
+
+	int n = 0; double mn = INFINITY, mx = -INFINITY;
+	each([&](double d) { ++n; mn = fmin(mn, d); mx = fmax(mx, d); });
+	block_sum_min_max(sm.red, n, mn, mx);
+	if (n <= 1) { if (tid == 0) *out = nan_d(); return; }  // reduce_mode([]) = NaN; one sample -> NaN
+
+	// std(ddof=1), two-pass like numpy
+	int nd = 0; double s1 = 0.0, dmy = 0.0;
+	each([&](double d) { s1 += d; });
+	block_sum3(sm.red, nd, s1, dmy);
+	const double mean = s1 / (double)n;
+	double ss = 0.0; dmy = 0.0; nd = 0;
+	each([&](double d) { const double e = d - mean; ss += e * e; });
+	block_sum3(sm.red, nd, ss, dmy);
+	const double sd = sqrt(ss / (double)(n - 1));
+
+	// scipy.stats.scoreatpercentile(x, 25 / 75): linear interpolation at (n-1)*p
+	double q[2];
+	for (int t = 0; t < 2; ++t) {
+		const double idx = (t == 0 ? 0.25 : 0.75) * (double)(n - 1);
+		const int i0 = (int)idx;
+		const double a0 = block_select(sm.sel, sm.red, each, i0, mn, mx);
+		if ((double)i0 == idx) q[t] = a0;
+		else {
+			const double a1 = block_select(sm.sel, sm.red, each, i0 + 1, mn, mx);
+			const double w0 = (double)(i0 + 1) - idx, w1 = idx - (double)i0;
+			q[t] = __dadd_rn(__dmul_rn(a0, w0), __dmul_rn(a1, w1)) / (w0 + w1);
+		}
+	}
+	const double iqr = (q[1] - q[0]) / 1.349;
+	const double sigma = (iqr > 0.0) ? fmin(sd, iqr) : sd;
+	const double bw = 1.0592238410488122 * sigma * pow((double)n, -0.2);
+	if (bw == 0.0) {
+		// "Selected KDE bandwidth is 0" -> np.median(x)  (backgrounds.py:28-32)
+		const double m1 = block_select(sm.sel, sm.red, each, (n - 1) >> 1, mn, mx);
+		double m2 = m1;
+		if ((n & 1) == 0) m2 = block_select(sm.sel, sm.red, each, n >> 1, mn, mx);
+		if (tid == 0) *out = 0.5 * (m1 + m2);
+		return;
+	}
+
+	const double a = mn - 3.0 * bw;
+	const double bb = mx + 3.0 * bw;
+	const double delta = (bb - a) / (double)(TBK_KDE_M - 1);
+	const double range = bb - a;
+
+	// linear binning (statsmodels linbin.fast_linbin); real part of x[] is the grid
+	for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i] = make_double2(0.0, 0.0);
+	__syncthreads();
+	each([&](double d) {
+		const double lxi = (d - a) / delta;
+		const int li = (int)lxi;
+		const double rem = lxi - (double)li;
+		if (li > 1 && li < TBK_KDE_M - 1) {
+			atomicAdd(&sm.x[li].x, 1.0 - rem);
+			atomicAdd(&sm.x[li + 1].x, rem);
+		}
+	});
+	__syncthreads();
+	// bit-reversal permutation + normalisation binned = g / (delta * nobs)
+	const double norm = 1.0 / (delta * (double)n);
+	for (int i = tid; i < TBK_KDE_M; i += nt) {
+		const int r = (int)(__brev((unsigned)i) >> 21);
+		if (i < r) { const double t = sm.x[i].x; sm.x[i].x = sm.x[r].x; sm.x[r].x = t; }
+	}
+	__syncthreads();
+	for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i].x *= norm;
+	__syncthreads();
+	kde_fft(sm.x, P.twiddle, false);
+	// silverman_transform: FAC_J = exp(-J^2 * 2 (pi bw / RANGE)^2) / (1 - (pi J / M)^2 / 3)
+	const double fac1 = 2.0 * (M_PI * bw / range) * (M_PI * bw / range);
+	for (int i = tid; i < TBK_KDE_M; i += nt) {
+		const int J = (i <= TBK_KDE_M / 2) ? i : TBK_KDE_M - i;
+		const double t = (double)J / (double)TBK_KDE_M * M_PI;
+		const double bc = 1.0 - 1.0 / 3.0 * (t * t);
+		const double fac = exp(-((double)J * (double)J * fac1)) / bc;
+		sm.x[i].x *= fac; sm.x[i].y *= fac;
+	}
+	__syncthreads();
+	// inverse: bit-reverse then DIT with conjugate twiddles
+	for (int i = tid; i < TBK_KDE_M; i += nt) {
+		const int r = (int)(__brev((unsigned)i) >> 21);
+		if (i < r) { const double2 t = sm.x[i]; sm.x[i] = sm.x[r]; sm.x[r] = t; }
+	}
+	__syncthreads();
+	kde_fft(sm.x, P.twiddle, true);
+	// argmax (first maximum) of the density
+	double bv = -INFINITY; int bi = 0x7fffffff;
+	for (int i = tid; i < TBK_KDE_M; i += nt) {
+		const double d = sm.x[i].x;
+		if (d > bv) { bv = d; bi = i; }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+		const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+		if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+	}
+	if ((tid & 31) == 0) { sm.bestv[tid >> 5] = bv; sm.besti[tid >> 5] = bi; }
+	__syncthreads();
+	if (tid == 0) {
+		for (int w = 1; w < nt / 32; ++w) {
+			if (sm.bestv[w] > bv || (sm.bestv[w] == bv && sm.besti[w] < bi)) { bv = sm.bestv[w]; bi = sm.besti[w]; }
+		}
+		// support = linspace(a, b, M): arange * step + start, last point = stop
+		const double g = (bi == TBK_KDE_M - 1) ? bb : __dadd_rn(__dmul_rn((double)bi, delta), a);
+		*out = g;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_radial_fit: move_median_central (utilities.py:52-62), drop NaNs, not-a-knot cubic spline
+// (InterpolatedUnivariateSpline k=3, backgrounds.py:186-197) in piecewise-polynomial form.
+__device__ double nanmedian_small(const double* x, int lo, int hi)
+{
+	double t[64];
+	int m = 0;
+	for (int i = lo; i < hi; ++i) {
+		const double d = x[i];
+		if (d == d) {
+			int j = m++;
+			while (j > 0 && t[j - 1] > d) { t[j] = t[j - 1]; --j; }
+			t[j] = d;
+		}
+	}
+	if (m == 0) return nan_d();
+	return (m & 1) ? t[m >> 1] : 0.5 * (t[(m >> 1) - 1] + t[m >> 1]);
+}
+
+struct RadialSmem {
+	double ky[TBK_MAX_RINGS], h[TBK_MAX_RINGS], dl[TBK_MAX_RINGS], dg[TBK_MAX_RINGS], du[TBK_MAX_RINGS],
+		rhs[TBK_MAX_RINGS], M2[TBK_MAX_RINGS];
+};
+
+// one CTA per FFI; the profile has <= TBK_MAX_RINGS points, so a single thread does the serial work
+__global__ void k_radial_fit(PlanDev P, Workspace ws, tbk_ffi_status* status, int round, int B)
+{
+	__shared__ RadialSmem rsm;
+	const int b = blockIdx.x;
+	if (b >= B || threadIdx.x != 0) return;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int n = P.nrings;
+	const double* raw = ws.s2_raw + (size_t)b * n;
+	double* s2 = ws.s2_hist + ((size_t)b * P.bkgiters + round) * n;
+	const int w = P.radial_smooth;
+	if (w > 0) {
+		// bottleneck.move_median(min_count=1) rolled by -w//2+1, then the edge fix-up loop
+		const int k = -(((-w) >> 1) + 1);  // python: -( (-w)//2 + 1 )
+		for (int i = 0; i < n; ++i) {
+			const int src = (i + k) % n;  // np.roll
+			s2[i] = nanmedian_small(raw, max(0, src - w + 1), src + 1);
+		}
+		for (int e = 0; e < w / 2 + 1; ++e) {
+			s2[e] = nanmedian_small(raw, 0, min(n, e + 2));
+			s2[n - 1 - e] = nanmedian_small(raw, max(0, n - (e + 2)), n);
+		}
+	} else {
+		for (int i = 0; i < n; ++i) s2[i] = raw[i];
+	}
+	// knots
+	int m = 0;
+	double* kx = c.kx;
+	double* ky = rsm.ky;
+	for (int i = 0; i < n; ++i) {
+		if (s2[i] == s2[i]) {
+			kx[m] = ring_center(P, i);  // bins[1:] - step/2
+			ky[m] = s2[i];
+			++m;
+		}
+	}
+	int ok = 0;
+	if (m >= 4) {
+		// second derivatives M_i of the not-a-knot cubic interpolant
+		double *h = rsm.h, *dl = rsm.dl, *dg = rsm.dg, *du = rsm.du, *rhs = rsm.rhs, *M2 = rsm.M2;
+		for (int i = 0; i < m - 1; ++i) h[i] = kx[i + 1] - kx[i];
+		const int nu = m - 2;  // unknowns M_1 .. M_{m-2}
+		for (int i = 1; i <= nu; ++i) {
+			dl[i] = h[i - 1]; dg[i] = 2.0 * (h[i - 1] + h[i]); du[i] = h[i];
+			rhs[i] = 6.0 * ((ky[i + 1] - ky[i]) / h[i] - (ky[i] - ky[i - 1]) / h[i - 1]);
+		}
+		// not-a-knot: M_0 = (1 + h0/h1) M_1 - (h0/h1) M_2 ; M_{m-1} likewise
+		{
+			const double r0 = h[0] / h[1];
+			dg[1] += dl[1] * (1.0 + r0);
+			du[1] -= dl[1] * r0;
+			const double r1 = h[m - 2] / h[m - 3];
+			dg[nu] += du[nu] * (1.0 + r1);
+			dl[nu] -= du[nu] * r1;
+		}
+		// Thomas algorithm
+		for (int i = 2; i <= nu; ++i) {
+			const double f = dl[i] / dg[i - 1];
+			dg[i] -= f * du[i - 1];
+			rhs[i] -= f * rhs[i - 1];
+		}
+		M2[nu] = rhs[nu] / dg[nu];
+		for (int i = nu - 1; i >= 1; --i) M2[i] = (rhs[i] - du[i] * M2[i + 1]) / dg[i];
+		M2[0] = (1.0 + h[0] / h[1]) * M2[1] - (h[0] / h[1]) * M2[2];
+		M2[m - 1] = (1.0 + h[m - 2] / h[m - 3]) * M2[m - 2] - (h[m - 2] / h[m - 3]) * M2[m - 3];
+		for (int i = 0; i < m - 1; ++i) {
+			c.pp[i][0] = ky[i];
+			c.pp[i][1] = (ky[i + 1] - ky[i]) / h[i] - h[i] * (2.0 * M2[i] + M2[i + 1]) / 6.0;
+			c.pp[i][2] = 0.5 * M2[i];
+			c.pp[i][3] = (M2[i + 1] - M2[i]) / (6.0 * h[i]);
+		}
+		// ring-centre interval -> spline piece
+		int s = 0;
+		for (int i = 0; i < n; ++i) {
+			const double cen = ring_center(P, i);
+			while (s + 1 < m - 1 && kx[s + 1] <= cen) ++s;
+			c.seg_of_ring[i] = (short)s;
+		}
+		c.x0 = kx[0]; c.xlast = kx[m - 1];
+		c.c_flat = exp10(ky[0]) - c.zp;
+		ok = 1;
+	}
+	// m == 3: FITPACK raises "m must be > k" (caught, backgrounds.py:192-194); m < 3: not enough points.
+	c.radial_ok = ok;
+	c.npts = m;
+	if (!ok) c.c_flat = 0.0;
+	if (status) {
+		status[b].n_ring_valid[round] = m;
+		status[b].radial_ok[round] = ok;
+		status[b].zeropoint[round] = c.zp;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_tile_round: sigma-clipped statistics of the non-flat meshes on x - radial(r) (backgrounds.py:200).
+__global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
+{
+	__shared__ TileSmem sm;
+	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int tile = P.nonflat_tiles[slot];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	const size_t img = (size_t)b * P.H * P.W;
+	const int lcol = tile_lcol(tid);
+	const int gx = tx * TBK_TILE + lcol;
+	double v[TBK_VPT];
+	unsigned valid = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int gy = ty * TBK_TILE + tile_lrow(tid, j);
+		const size_t off = img + (size_t)gy * P.W + gx;
+		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
+		const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + off));
+		const float x4[4] = {x.x, x.y, x.z, x.w};
+		const unsigned char m4[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			double d = 0.0;
+			if (!m4[q]) {
+				d = (double)x4[q] - radial_value(c, P, pixel_radius(P, gy, gx + q));
+				valid |= 1u << (4 * j + q);
+			}
+			v[4 * j + q] = d;
+		}
+	}
+	TileStat st = tile_sigma_clip<double>(v, valid, sm);
+	if (tid == 0) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_mesh_finalize: one CTA per FFI.  SExtractor estimator per mesh, mesh exclusion, IDW fill,
+// 3x3 nan-median, cubic-spline prefilter (photutils 1.3.0 Background2D).
+__device__ __forceinline__ double median_small(double* t, int m)
+{
+	for (int i = 1; i < m; ++i) {
+		const double d = t[i];
+		int j = i;
+		while (j > 0 && t[j - 1] > d) { t[j] = t[j - 1]; --j; }
+		t[j] = d;
+	}
+	return (m & 1) ? t[m >> 1] : 0.5 * (t[(m >> 1) - 1] + t[m >> 1]);
+}
+
+__global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
+	tbk_ffi_status* status, int round)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	double* val = reinterpret_cast<double*>(smraw);          // [ntiles] mesh statistic (NaN = excluded)
+	double* fil = val + P.ntiles;                            // [ntiles] filled / filtered mesh
+	double* tmp = fil + P.ntiles;                            // [ntiles] scratch
+	__shared__ RedSmem red;
+	__shared__ int s_nexcl;
+	const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int nt_tiles = P.ntiles, ny = P.ny, nx = P.nx;
+	if (tid == 0) s_nexcl = 0;
+	__syncthreads();
+
+	// (1) mesh statistic
+	int nexcl = 0;
+	for (int t = tid; t < nt_tiles; t += nt) {
+		TileStat st;
+		double shift = 0.0;
+		const int slot = P.use_radial ? P.tile_slot[t] : -1;
+		if (slot >= 0) st = ws.tile_nf[(size_t)b * P.n_nonflat + slot];
+		else { st = ws.tile_base[(size_t)b * nt_tiles + t]; shift = c.radial_ok ? c.c_flat : 0.0; }
+		const int nbad = TBK_NPIX_TILE - st.nfin;
+		double r = nan_d();
+		if (nbad <= TBK_NPIX_TILE / 2 && st.nfin > 0) {  // exclude_percentile = 50
+			const double mean = st.mean - shift, med = st.med - shift, sd = st.std;
+			r = 2.5 * med - 1.5 * mean;
+			if (sd == 0.0) r = mean;
+			else if (!(fabs(mean - med) / sd < 0.3)) r = med;
+		} else ++nexcl;
+		val[t] = r;
+	}
+	if (nexcl) atomicAdd(&s_nexcl, nexcl);
+	__syncthreads();
+	nexcl = s_nexcl;
+	if (status && tid == 0) { status[b].n_excluded[round] = nexcl; status[b].rounds = round + 1; }
+	if (nexcl == nt_tiles) {
+		// photutils raises ValueError("All meshes contain > ... masked pixels"); report and give NaN.
+		if (tid == 0) { c.no_good_mesh = 1; if (status) status[b].no_good_mesh = 1; }
+		return;
+	}
+
+	// (2) IDW fill of excluded meshes: 10 nearest good meshes by (distance^2, mesh index), weights 1/d
+	for (int t = tid; t < nt_tiles; t += nt) {
+		double r = val[t];
+		if (nexcl && !(r == r)) {
+			const int iy = t / nx, ix = t % nx;
+			int bd[10]; int bi[10]; int m = 0;
+			for (int g = 0; g < nt_tiles; ++g) {
+				const double gv = val[g];
+				if (!(gv == gv)) continue;
+				const int dy = g / nx - iy, dx = g % nx - ix;
+				const int d2 = dy * dy + dx * dx;
+				if (m < 10 || d2 < bd[m - 1]) {
+					int j = (m < 10) ? m++ : 9;
+					while (j > 0 && bd[j - 1] > d2) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+					bd[j] = d2; bi[j] = g;
+				}
+			}
+			double sw = 0.0, swv = 0.0;
+			for (int j = 0; j < m; ++j) {
+				const double wgt = 1.0 / sqrt((double)bd[j]);
+				sw += wgt; swv += wgt * val[bi[j]];
+			}
+			r = swv / sw;
+		}
+		fil[t] = r;
+	}
+	__syncthreads();
+
+	// (3) 3x3 nan-median, NaN padding (generic_filter(nanmedian, mode='constant', cval=nan))
+	for (int t = tid; t < nt_tiles; t += nt) {
+		const int iy = t / nx, ix = t % nx;
+		double w9[9]; int m = 0;
+		for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+			const int yy = iy + dy, xx = ix + dx;
+			if (yy >= 0 && yy < ny && xx >= 0 && xx < nx) { const double d = fil[yy * nx + xx]; if (d == d) w9[m++] = d; }
+		}
+		tmp[t] = m ? median_small(w9, m) : nan_d();
+	}
+	__syncthreads();
+	double mn = INFINITY, mx = -INFINITY; int dummy = 0;
+	double* hist = ws.mesh_hist + ((size_t)b * P.bkgiters + round) * nt_tiles;
+	for (int t = tid; t < nt_tiles; t += nt) { mn = fmin(mn, tmp[t]); mx = fmax(mx, tmp[t]); hist[t] = tmp[t]; }
+	block_sum_min_max(red, dummy, mn, mx);
+	if (tid == 0) { c.mesh_min = mn; c.mesh_max = mx; c.mesh_const = (mx - mn == 0.0) ? 1 : 0; }
+
+	// (4) cubic B-spline prefilter, mode='reflect' (scipy ni_splines.c), axis 0 then axis 1
+	const double z = sqrt(3.0) - 2.0;
+	const double gain = (1.0 - z) * (1.0 - 1.0 / z);
+	for (int axis = 0; axis < 2; ++axis) {
+		const int nlines = axis == 0 ? nx : ny;
+		const int len = axis == 0 ? ny : nx;
+		const int stride = axis == 0 ? nx : 1;
+		const int lstep = axis == 0 ? 1 : nx;
+		for (int l = tid; l < nlines; l += nt) {
+			double* p = tmp + (size_t)l * lstep;
+			if (len > 1) {
+				for (int i = 0; i < len; ++i) p[i * stride] *= gain;
+				// _init_causal_reflect
+				const double zn = pow(z, (double)len);
+				const double c0 = p[0];
+				double zi = z;
+				double acc = p[0] + zn * p[(len - 1) * stride];
+				for (int i = 1; i < len; ++i) {
+					acc += zi * (p[i * stride] + zn * p[(len - 1 - i) * stride]);
+					zi *= z;
+				}
+				acc *= z / (1.0 - zn * zn);
+				acc += c0;
+				p[0] = acc;
+				for (int i = 1; i < len; ++i) p[i * stride] += z * p[(i - 1) * stride];
+				// _init_anticausal_reflect
+				p[(len - 1) * stride] *= z / (z - 1.0);
+				for (int i = len - 2; i >= 0; --i) p[i * stride] = z * (p[(i + 1) * stride] - p[i * stride]);
+			}
+		}
+		__syncthreads();
+	}
+	double* coef = ws.coef + (size_t)b * nt_tiles;
+	for (int t = tid; t < nt_tiles; t += nt) coef[t] = tmp[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_final: bkg = img_bkg_radial + img_bkg_square (backgrounds.py:209), float32.
+__global__ void __launch_bounds__(TBK_NT) k_final(PlanDev P, Workspace ws,
+	float* __restrict__ bkg, uint8_t* __restrict__ mask_out)
+{
+	__shared__ ZoomTile z;
+	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const FfiCtl& c = ws.ctl[b];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	const size_t img = (size_t)b * P.H * P.W;
+	const int lcol = tile_lcol(tid);
+	const int gx = tx * TBK_TILE + lcol;
+	if (c.all_masked || c.no_good_mesh) {
+		const float q = nan_f();
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const size_t off = img + (size_t)(ty * TBK_TILE + tile_lrow(tid, j)) * P.W + gx;
+			*reinterpret_cast<float4*>(bkg + off) = make_float4(q, q, q, q);
+			if (c.all_masked) *reinterpret_cast<uchar4*>(mask_out + off) = make_uchar4(1, 1, 1, 1);
+		}
+		return;
+	}
+	zoom_tile_load(z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
+	__syncthreads();
+	const bool nonflat = P.use_radial && c.radial_ok && P.tile_slot[tile] >= 0;
+	const double cflat = (P.use_radial && c.radial_ok) ? c.c_flat : 0.0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int lrow = tile_lrow(tid, j);
+		const int gy = ty * TBK_TILE + lrow;
+		double sq[4];
+		zoom_eval4(z, P.zoom_w, lrow, lcol, sq);
+		float o[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const double rad = nonflat ? radial_value(c, P, pixel_radius(P, gy, gx + q)) : cflat;
+			o[q] = (float)(rad + zoom_clip(c, sq[q]));
+		}
+		const size_t off = img + (size_t)gy * P.W + gx;
+		*reinterpret_cast<float4*>(bkg + off) = make_float4(o[0], o[1], o[2], o[3]);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline bool launch_ok(const char* what)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("%s: %s", what, cudaGetErrorString(e)); return false; }
+	return true;
+}
+
+int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
+	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
+	tbk_ffi_status* status, cudaStream_t st)
+{
+	const dim3 gt(P.ntiles, B);
+	const int gb = (B + 127) / 128;
+	k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B);
+	k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask);
+	k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B);
+	if (!launch_ok("base")) return TBK_ERR_CUDA;
+	const size_t mesh_smem = 3 * (size_t)P.ntiles * sizeof(double);
+	for (int round = 0; round < P.bkgiters; ++round) {
+		if (P.use_radial) {
+			if (round > 0) {
+				k_zp_min<<<gt, TBK_NT, 0, st>>>(P, ws, cube, mask);
+				k_set_zp<<<gb, 128, 0, st>>>(ws, B);
+			}
+			k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round);
+			k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws);
+			k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B);
+			if (P.n_nonflat > 0)
+				k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask);
+		}
+		k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round);
+		if (!launch_ok("round")) return TBK_ERR_CUDA;
+	}
+	k_final<<<gt, TBK_NT, 0, st>>>(P, ws, bkg, mask);
+	if (!launch_ok("final")) return TBK_ERR_CUDA;
+	return TBK_OK;
+}
+
+int tbk_fit_configure(void)
+{
+	cudaError_t e = cudaFuncSetAttribute(k_ring_kde, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KdeSmem));
+	if (e != cudaSuccess) { tbk_set_error("cudaFuncSetAttribute(k_ring_kde): %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	e = cudaFuncSetAttribute(k_mesh_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * (int)sizeof(double));
+	if (e != cudaSuccess) { tbk_set_error("cudaFuncSetAttribute(k_mesh_finalize): %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}

@@ -1,0 +1,24 @@
+// tbk_internal.h -- host-side declarations shared by the translation units of libtbk.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/tbk.h"
+
+struct PlanDev;
+struct Workspace;
+
+void tbk_set_error(const char* fmt, ...);
+
+// tbk_fit.cu
+int tbk_fit_configure(void);
+int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
+	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
+	tbk_ffi_status* status, cudaStream_t st);
+
+// tbk_prepare.cu
+int tbk_launch_time_smooth(int H, int W, const float* bkg, int n, int w,
+	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi, float* out, cudaStream_t st);
+int tbk_launch_sum_accumulate(const PlanDev& P, const float* cube, const float* bkg_smooth,
+	uint8_t* flags, const tbk_ffi_meta* meta, int n, float* flux_out,
+	double* sum, int32_t* nimg, int32_t* used, int* zero_flags, cudaStream_t st);
+int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg, const int32_t* used,
+	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, cudaStream_t st);

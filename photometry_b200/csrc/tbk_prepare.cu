@@ -1,0 +1,160 @@
+// tbk_prepare.cu -- the prepare-stage loops around fit_background: background time smoothing
+// (photometry/prepare.py:317-335) and the fused final per-image loop / sumimage accumulation
+// (prepare.py:408-470).  Pure streaming kernels: HBM-bound, float4 / uchar4 accesses.
+#include "tbk_common.cuh"
+#include "tbk_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// out[k] = bottleneck.nanmean(float32 block[k-w .. k+w], axis=2): float32 accumulator, frames added
+// in index order, divided by the non-NaN count (all-NaN -> NaN).  Grid: x = cadence (fastest, so the
+// 2w+1 CTAs that share an input line run together and hit L2), y = pixel chunk.
+__device__ __forceinline__ void nanacc(float v, float& s, int& c) { if (v == v) { s += v; ++c; } }
+
+__global__ void __launch_bounds__(256) k_time_smooth(size_t npix4, const float4* __restrict__ bkg, int n, int w,
+	const float4* __restrict__ halo_lo, int n_lo, const float4* __restrict__ halo_hi, int n_hi,
+	float4* __restrict__ out)
+{
+	const int k = blockIdx.x;
+	const size_t p = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
+	if (p >= npix4) return;
+	float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+	int cx = 0, cy = 0, cz = 0, cw = 0;
+	for (int j = k - w; j <= k + w; ++j) {
+		const float4* src;
+		if (j < 0) { if (n_lo + j < 0) continue; src = halo_lo + (size_t)(n_lo + j) * npix4; }
+		else if (j >= n) { if (j - n >= n_hi) continue; src = halo_hi + (size_t)(j - n) * npix4; }
+		else src = bkg + (size_t)j * npix4;
+		const float4 v = __ldg(src + p);
+		nanacc(v.x, s.x, cx); nanacc(v.y, s.y, cy); nanacc(v.z, s.z, cz); nanacc(v.w, s.w, cw);
+	}
+	float4 o;
+	o.x = cx ? s.x / (float)cx : nan_f();
+	o.y = cy ? s.y / (float)cy : nan_f();
+	o.z = cz ? s.z / (float)cz : nan_f();
+	o.w = cw ? s.w / (float)cw : nan_f();
+	out[(size_t)k * npix4 + p] = o;
+}
+
+int tbk_launch_time_smooth(int H, int W, const float* bkg, int n, int w,
+	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi, float* out, cudaStream_t st)
+{
+	const size_t npix4 = (size_t)H * W / 4;
+	dim3 grid(n, (unsigned)((npix4 + 255) / 256));
+	k_time_smooth<<<grid, 256, 0, st>>>(npix4, (const float4*)bkg, n, w, (const float4*)halo_lo, n_lo,
+		(const float4*)halo_hi, n_hi, (float4*)out);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_time_smooth: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "Whole image is zero" manual exclude (pixel_flags.py:54-56): zero_flags[k] = 1 unless some pixel != 0.
+__global__ void k_zero_init(int* zero_flags, int n)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) zero_flags[k] = 1;
+}
+__global__ void __launch_bounds__(256) k_zero_detect(size_t npix4, const float4* __restrict__ cube, int* zero_flags)
+{
+	const int k = blockIdx.y;
+	bool nz = false;
+	for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix4; p += (size_t)gridDim.x * blockDim.x) {
+		const float4 v = __ldg(cube + (size_t)k * npix4 + p);
+		nz |= !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
+	}
+	if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) zero_flags[k] = 0;
+}
+
+// One thread owns four horizontally adjacent pixels and walks the cadence axis; the accumulators
+// stay in registers and are folded into the caller's running sums at the end.
+__global__ void __launch_bounds__(256) k_sum_accumulate(PlanDev P, const float4* __restrict__ cube,
+	const float4* __restrict__ bkg, uchar4* flags, const tbk_ffi_meta* __restrict__ meta,
+	const int* __restrict__ zero_flags, int n, float4* flux_out,
+	double* sum, int32_t* nimg, int32_t* used)
+{
+	const size_t npix4 = (size_t)P.H * P.W / 4;
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npix4) return;
+	const int gx = (int)((p * 4) % P.W);
+	double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+	int n0 = 0, n1 = 0, n2 = 0, n3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+	for (int k = 0; k < n; ++k) {
+		const tbk_ffi_meta m = meta[k];
+		bool excl_all = false, excl_cols = false;
+		if (P.is_tess) {
+			const double time = 0.5 * (m.tstart + m.tstop);
+			const int cad = m.cadenceno;
+			if (P.camera == 1 && P.ccd == 4 && (cad <= 4724 || m.tstart <= 1325.881282301840)) excl_cols = gx >= 1536;
+			else if (P.camera == 1 && ((cad >= 11354 && cad <= 11366) || (time >= 1464.0158778 && time <= 1464.265871))) excl_all = true;
+			if (zero_flags[k]) excl_all = true;
+		}
+		const size_t o = (size_t)k * npix4 + p;
+		uchar4 f = flags[o];
+		if (excl_all || excl_cols) {
+			f.x |= 2; f.y |= 2; f.z |= 2; f.w |= 2;   // PixelQualityFlags.ManualExclude
+			flags[o] = f;
+		}
+		float4 x = __ldg(cube + o);
+		if (!m.backapp) {
+			const float4 bk = __ldg(bkg + o);
+			x.x -= bk.x; x.y -= bk.y; x.z -= bk.z; x.w -= bk.w;
+		}
+		if (f.x & 2) x.x = nan_f();
+		if (f.y & 2) x.y = nan_f();
+		if (f.z & 2) x.z = nan_f();
+		if (f.w & 2) x.w = nan_f();
+		if (flux_out) flux_out[o] = x;
+		if ((m.dquality & 4335) == 0) {   // TESSQualityFlags.DEFAULT_BITMASK (quality.py:123-124)
+			n0 += isfinite(x.x) ? 1 : 0; n1 += isfinite(x.y) ? 1 : 0; n2 += isfinite(x.z) ? 1 : 0; n3 += isfinite(x.w) ? 1 : 0;
+			s0 += (x.x == x.x) ? (double)x.x : 0.0;
+			s1 += (x.y == x.y) ? (double)x.y : 0.0;
+			s2 += (x.z == x.z) ? (double)x.z : 0.0;
+			s3 += (x.w == x.w) ? (double)x.w : 0.0;
+		}
+		u0 += (f.x & 1) == 0; u1 += (f.y & 1) == 0; u2 += (f.z & 1) == 0; u3 += (f.w & 1) == 0;
+	}
+	double* sp = sum + p * 4; int32_t* np_ = nimg + p * 4; int32_t* up = used + p * 4;
+	sp[0] += s0; sp[1] += s1; sp[2] += s2; sp[3] += s3;
+	np_[0] += n0; np_[1] += n1; np_[2] += n2; np_[3] += n3;
+	up[0] += u0; up[1] += u1; up[2] += u2; up[3] += u3;
+}
+
+int tbk_launch_sum_accumulate(const PlanDev& P, const float* cube, const float* bkg_smooth,
+	uint8_t* flags, const tbk_ffi_meta* meta, int n, float* flux_out,
+	double* sum, int32_t* nimg, int32_t* used, int* zero_flags, cudaStream_t st)
+{
+	const size_t npix4 = (size_t)P.H * P.W / 4;
+	k_zero_init<<<(n + 255) / 256, 256, 0, st>>>(zero_flags, n);
+	if (P.is_tess) {
+		dim3 g(148 * 2, n);
+		k_zero_detect<<<g, 256, 0, st>>>(npix4, (const float4*)cube, zero_flags);
+	} else {
+		cudaMemsetAsync(zero_flags, 0, sizeof(int) * n, st);
+	}
+	k_sum_accumulate<<<(unsigned)((npix4 + 255) / 256), 256, 0, st>>>(P, (const float4*)cube,
+		(const float4*)bkg_smooth, (uchar4*)flags, meta, zero_flags, n, (float4*)flux_out, sum, nimg, used);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_sum_accumulate: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sum_finalize(size_t npix, const double* __restrict__ sum,
+	const int32_t* __restrict__ nimg, const int32_t* __restrict__ used, int numfiles, double threshold,
+	double* __restrict__ sumimage, uint8_t* __restrict__ pixels_used)
+{
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npix) return;
+	sumimage[p] = sum[p] / (double)nimg[p];                       // SumImage /= Nimg (0/0 -> NaN)
+	pixels_used[p] = ((double)used[p] / (double)numfiles > threshold) ? 1 : 0;
+}
+
+int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg, const int32_t* used,
+	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, cudaStream_t st)
+{
+	const size_t npix = (size_t)H * W;
+	k_sum_finalize<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(npix, sum, nimg, used, numfiles, threshold, sumimage, pixels_used);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_sum_finalize: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}

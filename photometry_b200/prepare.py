@@ -1,0 +1,118 @@
+"""
+The hot loops of ``photometry.prepare.prepare_photometry`` around ``fit_background`` on device-resident
+FFI stacks (photometry/prepare.py:265-470): per-FFI background fit, background time smoothing, the
+final per-image loop and the sumimage / Nimg / UsedInBackgrounds accumulation.
+
+Multi-GPU: one process per GPU; each rank owns a contiguous block of the cadence axis
+(:func:`shard_bounds`).  The only exchanges are (1) ``w = time_smooth // 2`` edge frames with each
+neighbour for the smoothing window and (2) one sum-reduce of the three accumulators to rank 0.
+"""
+from dataclasses import dataclass
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world_size, rank):
+	"""Contiguous cadence block [lo, hi) of ``rank`` (GPU g gets [g*N/G, (g+1)*N/G))."""
+	return (rank * n) // world_size, ((rank + 1) * n) // world_size
+
+
+def exchange_halos(frames, w, group=None):
+	"""
+	Exchange the ``w`` edge frames of ``frames`` [n_local, H, W] with the previous / next rank.
+	Returns ``(halo_lo, halo_hi)`` (None at the ends of the sector or when not distributed).
+	Works on CUDA tensors (NCCL) and CPU tensors (gloo).
+	"""
+	if w <= 0 or not (dist.is_available() and dist.is_initialized()):
+		return None, None
+	rank, world = dist.get_rank(group), dist.get_world_size(group)
+	if world == 1:
+		return None, None
+	if frames.shape[0] < w:
+		raise ValueError(f"shard of {frames.shape[0]} cadences is shorter than the smoothing half-width {w}")
+	ops = []
+	halo_lo = halo_hi = None
+	to_global = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+	if rank > 0:
+		halo_lo = torch.empty((w,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
+		ops.append(dist.P2POp(dist.isend, frames[:w].contiguous(), to_global(rank - 1), group))
+		ops.append(dist.P2POp(dist.irecv, halo_lo, to_global(rank - 1), group))
+	if rank < world - 1:
+		halo_hi = torch.empty((w,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
+		ops.append(dist.P2POp(dist.isend, frames[-w:].contiguous(), to_global(rank + 1), group))
+		ops.append(dist.P2POp(dist.irecv, halo_hi, to_global(rank + 1), group))
+	for req in dist.batch_isend_irecv(ops):
+		req.wait()
+	return halo_lo, halo_hi
+
+
+def reduce_accumulators(sum_, nimg, used, n_local, group=None):
+	"""Sum-reduce SumImage / Nimg / UsedInBackgrounds to rank 0 and return the global file count."""
+	if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+		return n_local
+	dst = dist.get_global_rank(group, 0) if group is not None else 0
+	dist.reduce(sum_, dst=dst, op=dist.ReduceOp.SUM, group=group)
+	dist.reduce(nimg, dst=dst, op=dist.ReduceOp.SUM, group=group)
+	dist.reduce(used, dst=dst, op=dist.ReduceOp.SUM, group=group)
+	cnt = torch.tensor([n_local], dtype=torch.int64, device=sum_.device)
+	dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+	return int(cnt.item())
+
+
+@dataclass
+class SectorResult:
+	"""Device-resident products of one (shard of a) sector/camera/CCD stack; names follow the HDF5 layout."""
+	backgrounds_unsmoothed: torch.Tensor  # float32 [n, H, W]  (temp file group of the reference)
+	backgrounds: torch.Tensor             # float32 [n, H, W]  backgrounds/NNNN
+	pixel_flags: torch.Tensor             # uint8   [n, H, W]  pixel_flags/NNNN
+	images: torch.Tensor                  # float32 [n, H, W]  images/NNNN (background subtracted) or None
+	sumimage: torch.Tensor                # float64 [H, W]     (rank 0; None elsewhere)
+	backgrounds_pixels_used: torch.Tensor # uint8   [H, W]     (rank 0; None elsewhere)
+	nimg: torch.Tensor                    # int32   [H, W]     reduced on rank 0
+	used: torch.Tensor                    # int32   [H, W]     reduced on rank 0
+	status: np.ndarray                    # tbk_ffi_status per local FFI
+	numfiles: int                         # global number of cadences
+
+
+def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, keep_images=True,
+	backgrounds_pixels_threshold=0.5, group=None):
+	"""
+	Run prepare.py:265-470 for this rank's shard.
+
+	fitter      :class:`photometry_b200.BackgroundFitter` for the stack's shape / camera / ccd
+	cube        float32 CUDA tensor [n_local, H, W], time ordered
+	meta        ``tbk_ffi_meta`` numpy array [n_local]
+	time_smooth smoothing window in cadences (prepare.py:258: 3 at 1800 s, 9 at 600 s)
+	chunk       FFIs per ``tbk_fit_batch`` launch
+	"""
+	from ._lib import STATUS_DTYPE
+	n = cube.shape[0]
+	dev = cube.device
+	meta = np.ascontiguousarray(meta)
+	meta_d = fitter.meta_to_device(meta)
+	isz = meta.dtype.itemsize
+	bkg_us = torch.empty_like(cube)
+	flags = torch.empty(cube.shape, dtype=torch.uint8, device=dev)
+	status = torch.empty(n * STATUS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+	ssz = STATUS_DTYPE.itemsize
+	for i in range(0, n, chunk):
+		j = min(i + chunk, n)
+		fitter.fit(cube[i:j], meta_d[i * isz:j * isz], None if extra_mask is None else extra_mask[i:j],
+			bkg_out=bkg_us[i:j], mask_out=flags[i:j], status_out=status[i * ssz:j * ssz])
+	w = int(time_smooth) // 2
+	halo_lo, halo_hi = exchange_halos(bkg_us, w, group)
+	bkg = fitter.time_smooth(bkg_us, w, halo_lo, halo_hi)
+	H, W = cube.shape[1:]
+	sum_ = torch.zeros((H, W), dtype=torch.float64, device=dev)
+	nimg = torch.zeros((H, W), dtype=torch.int32, device=dev)
+	used = torch.zeros((H, W), dtype=torch.int32, device=dev)
+	images = torch.empty_like(cube) if keep_images else None
+	fitter.sum_accumulate(cube, bkg, flags, meta_d, sum_, nimg, used, flux_out=images)
+	numfiles = reduce_accumulators(sum_, nimg, used, n, group)
+	is_root = not (dist.is_available() and dist.is_initialized()) or dist.get_rank(group) == 0
+	sumimage = pixels_used = None
+	if is_root:
+		sumimage, pixels_used = fitter.sum_finalize(sum_, nimg, used, numfiles, backgrounds_pixels_threshold)
+	return SectorResult(bkg_us, bkg, flags, images, sumimage, pixels_used, nimg, used,
+		status.cpu().numpy().view(STATUS_DTYPE), numfiles)
