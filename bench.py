@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""
+bench.py -- FFIs/sec background-fitted (2048 x 2048) on N B200 GPUs, and % of the HBM roofline.
+
+Workload (BASELINE.json configs[1]): a synthetic single-CCD 30-min-cadence sector, 2048 x 2048 x 1,340
+FFIs per GPU (camera 1, ccd 2, TESS path: 3 rounds of radial + mesh background).  One "step" = one
+pass of ``fit_background`` over the whole device-resident 1,340-FFI cube (22.5 GB, far larger than the
+126 MB L2, so every step streams from HBM).  With N > 1 every rank fits its own 1,340-FFI stack
+(cadence shards need no exchange inside the fit), i.e. weak scaling.
+
+Keys beyond the base contract: ``roofline`` (dominant kernel, CUDA-event timed), ``cpu_baseline``
+(the CPU oracle under the reference's spawn-Pool driver on this box's cores), ``kernel_ms`` (device
+time per kernel class for one step), ``prepare_path`` (fit + time smoothing + sumimage accumulation
+[+ NCCL reduce], FFIs/s).
+
+``--impl reference`` times the reference's CPU path (restated oracle; the reference itself cannot be
+imported here) with all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_FFI = 2048 * 2048 * (4 + 4 + 1)  # image read + background write + mask write
+H = W = 2048
+CAMERA, CCD = 1, 2
+SEED = 20260117 + 1
+
+
+def load_peaks():
+	path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+	if os.path.exists(path):
+		with open(path) as fid:
+			return float(json.load(fid)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+	return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+	"""nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+	Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+	def __init__(self, index):
+		self.index = index
+		self.lines = []
+		self.proc = None
+
+	def start(self):
+		try:
+			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+				'--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+			self.thread = threading.Thread(target=self._read, daemon=True)
+			self.thread.start()
+		except OSError:
+			self.proc = None
+
+	def _read(self):
+		for line in self.proc.stdout:
+			self.lines.append(line.strip())
+
+	def stop(self):
+		if self.proc is None:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+		self.proc.terminate()
+		try:
+			self.proc.wait(timeout=5)
+		except Exception:
+			self.proc.kill()
+		sm, mx, reasons = [], [], set()
+		names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+		for ln in self.lines:
+			f = [x.strip() for x in ln.split(',')]
+			if len(f) < 7:
+				continue
+			try:
+				sm.append(float(f[0])); mx.append(float(f[1]))
+			except ValueError:
+				continue
+			for nm, v in zip(names, f[3:7]):
+				if v.lower().startswith('active'):
+					reasons.add(nm)
+		sm.sort()
+		return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+			"samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+	img, hdr = args
+	import oracle
+	bkg, mask = oracle.fit_background(oracle.FFIImageLite(img, hdr, True), discarded_bins=True)
+	return float(bkg[0, 0]), int(mask.sum())
+
+
+def cpu_reference_run(images, headers, cores):
+	"""The reference's driver shape (prepare.py:184-199, 291): spawn Pool(cores).imap over the FFIs."""
+	import multiprocessing
+	ctx = multiprocessing.get_context('spawn')
+	items = list(zip(images, headers))
+	with ctx.Pool(cores) as pool:
+		list(pool.imap(_oracle_worker, items[:cores]))  # warm-up: interpreter start + imports
+		t0 = time.perf_counter()
+		list(pool.imap(_oracle_worker, items))
+		dt = time.perf_counter() - t0
+	return len(items) / dt, dt
+
+
+def make_headers(n):
+	return [dict(CAMERA=CAMERA, CCD=CCD, TSTART=1400.0 + k * 1800 / 86400, TSTOP=1400.0 + (k + 1) * 1800 / 86400,
+		FFIINDEX=9000 + k, DQUALITY=(32 if k % 37 == 5 else 0)) for k in range(n)]
+
+
+def host_sample(n):
+	"""n synthetic FFIs of the benchmark workload as host arrays (generated on the GPU when there is one)."""
+	import torch
+	from photometry_b200 import synth
+	if torch.cuda.is_available():
+		cube = synth.synth_stack_torch(n, H, W, torch.device('cuda'), camera=CAMERA, ccd=CCD, seed=SEED)
+		return cube.cpu().numpy()
+	return synth.synth_stack_numpy(n, H, W, camera=CAMERA, ccd=CCD, seed=SEED)
+
+
+def run_reference(args):
+	rank = int(os.environ.get('RANK', '0'))
+	if rank != 0:
+		return
+	cores = os.cpu_count() or 1
+	per_step = max(cores, 8) if args.ref_ffis is None else args.ref_ffis
+	imgs = host_sample(per_step)
+	hdrs = make_headers(per_step)
+	import multiprocessing
+	ctx = multiprocessing.get_context('spawn')
+	items = list(zip(list(imgs), hdrs))
+	with ctx.Pool(cores) as pool:
+		for _ in range(max(args.warmup, 1) if args.warmup else 0):
+			list(pool.imap(_oracle_worker, items[:cores]))
+		t0 = time.perf_counter()
+		for _ in range(args.steps):
+			list(pool.imap(_oracle_worker, items))
+		dt = time.perf_counter() - t0
+	value = per_step * args.steps / dt
+	sample = f"{per_step} FFIs per step x {args.steps} steps of the same synthetic 2048x2048 workload, spawn Pool({cores}).imap, in-memory float32 inputs"
+	line = {
+		"impl": "reference", "metric": "FFIs/sec background-fitted (2048x2048)", "value": value, "unit": "FFIs/s",
+		"n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+		"higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+		"config": {"workload": "synthetic single CCD 2048x2048 x 1,340 FFIs (30-min cadence sector), bounded sample", "sample_ffis_per_step": per_step},
+		"cpu_baseline": {"value": value, "unit": "FFIs/s", "cores": cores, "kind": "port", "sample": sample},
+		"e2e": {"value": value, "unit": "FFIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+		"gpu_launches": 0,
+	}
+	print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+	import numpy as np
+	import torch
+	import torch.distributed as dist
+	import photometry_b200 as pb
+	from photometry_b200 import synth, _lib
+	import __graft_entry__
+	rank = int(os.environ.get('RANK', '0'))
+	world = int(os.environ.get('WORLD_SIZE', '1'))
+	local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+	if not torch.cuda.is_available():
+		raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+	torch.cuda.set_device(local_rank)
+	dev = torch.device('cuda', local_rank)
+	if rank == 0:
+		__graft_entry__.build()
+	if world > 1:
+		os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+		dist.init_process_group('nccl', device_id=dev)
+		dist.barrier()
+	n = args.ffis
+	chunk = args.chunk
+	cube = synth.synth_stack_torch(n, H, W, dev, camera=CAMERA, ccd=CCD, seed=SEED + rank)
+	hdrs = make_headers(n)
+	meta = pb.meta_from_headers(hdrs)
+	fit = pb.BackgroundFitter((H, W), True, CAMERA, CCD, device=local_rank)
+	meta_d = fit.meta_to_device(meta)
+	isz = meta.dtype.itemsize
+	bkg = torch.empty_like(cube)
+	mask = torch.empty(cube.shape, dtype=torch.uint8, device=dev)
+	lib = _lib.load()
+
+	def step():
+		for a in range(0, n, chunk):
+			b = min(a + chunk, n)
+			fit.fit(cube[a:b], meta_d[a * isz:b * isz], bkg_out=bkg[a:b], mask_out=mask[a:b])
+
+	def barrier():
+		torch.cuda.synchronize(dev)
+		if world > 1:
+			dist.barrier()
+			torch.cuda.synchronize(dev)
+
+	for _ in range(args.warmup):
+		step()
+	barrier()
+	sampler = ClockSampler(local_rank)
+	if rank == 0:
+		sampler.start()
+	l0 = lib.tbk_launch_count()
+	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	e0.record()
+	for _ in range(args.steps):
+		step()
+	e1.record()
+	barrier()
+	launches = int(lib.tbk_launch_count() - l0)
+	ms = e0.elapsed_time(e1)
+	clocks = sampler.stop() if rank == 0 else None
+	if world > 1:
+		t = torch.tensor([ms], dtype=torch.float64, device=dev)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		ms = float(t.item())
+		lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+		dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+		launches = int(lt.item())
+	value = world * n * args.steps / (ms * 1e-3)
+
+	# ---- per-kernel device times for one step (events between launches) -> roofline of the dominant kernel
+	prof = {}
+	for a in range(0, n, chunk):
+		b = min(a + chunk, n)
+		fit.fit(cube[a:b], meta_d[a * isz:b * isz], bkg_out=bkg[a:b], mask_out=mask[a:b], profile=prof)
+	ncalls = (n + chunk - 1) // chunk
+	dom = max((k for k in prof if k != 'misc'), key=lambda k: prof[k])
+	launches_per_call = {'tile_base': 1, 'tile_round': 3, 'zp_min': 2, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
+	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
+	peak, peak_src = load_peaks()
+	achieved = ALGO_BYTES_PER_FFI * min(chunk, n) / (dom_launch_ms * 1e-3) / 1e9
+	roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+		"traffic": None, "peak_source": peak_src, "launch_ms": dom_launch_ms, "ffis_per_launch": min(chunk, n),
+		"whole_path_achieved": value / world * ALGO_BYTES_PER_FFI / 1e9, "whole_path_frac": value / world * ALGO_BYTES_PER_FFI / 1e9 / peak}
+
+	# ---- end to end: pinned host stack -> device -> fit -> pinned host results (same metric)
+	ne = min(args.e2e_ffis, n)
+	host_in = torch.empty((ne, H, W), dtype=torch.float32).pin_memory()
+	host_in.copy_(cube[:ne])
+	host_bkg = torch.empty((ne, H, W), dtype=torch.float32).pin_memory()
+	host_mask = torch.empty((ne, H, W), dtype=torch.uint8).pin_memory()
+	reps = max(1, n // ne)   # cycle the pinned sample so that one e2e step also covers ~n FFIs
+	def e2e_step():
+		hb = db = 0
+		for _ in range(reps):
+			h, d = pb.fit_stack_host(fit, host_in, meta[:ne], host_bkg, host_mask, chunk=min(chunk, ne))
+			hb += h; db += d
+		return hb, db
+	for _ in range(min(args.warmup, 2)):
+		e2e_step()
+	barrier()
+	esteps = max(1, min(args.steps, 3))
+	f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	f0.record()
+	for _ in range(esteps):
+		h2d, d2h = e2e_step()
+	f1.record()
+	barrier()
+	ems = f0.elapsed_time(f1)
+	if world > 1:
+		t = torch.tensor([ems], dtype=torch.float64, device=dev)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		ems = float(t.item())
+	e2e_value = world * reps * ne * esteps / (ems * 1e-3)
+	# spot-check the transferred result against the resident one
+	assert torch.equal(host_bkg[0], bkg[0].cpu()) or torch.allclose(host_bkg[0], bkg[0].cpu(), rtol=1e-6, equal_nan=True)
+	del host_in, host_bkg, host_mask
+
+	# ---- prepare path: fit + time smoothing + sumimage accumulation (+ NCCL reduce)
+	prep = None
+	if args.prepare:
+		np_ = min(n, args.prepare_ffis)
+		barrier()
+		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True)
+		barrier()
+		g0.record()
+		res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True)
+		g1.record()
+		barrier()
+		pms = g0.elapsed_time(g1)
+		if world > 1:
+			t = torch.tensor([pms], dtype=torch.float64, device=dev)
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+			pms = float(t.item())
+		prep = {"value": world * np_ / (pms * 1e-3), "unit": "FFIs/s", "ffis_per_gpu": np_, "numfiles": res.numfiles,
+			"stages": "fit + time_smooth(w=1) + sum_accumulate + reduce + finalize"}
+		del res
+
+	if rank != 0:
+		if world > 1:
+			dist.destroy_process_group()
+		return
+
+	# ---- CPU baseline on this box's host cores (rank 0, N = 1 only; bounded sample)
+	cpu = None
+	if world == 1 and not args.no_cpu:
+		cores = os.cpu_count() or 1
+		ns = min(max(cores, 8), 64)
+		imgs = cube[:ns].cpu().numpy()
+		try:
+			v, dt = cpu_reference_run(list(imgs), hdrs[:ns], cores)
+			cpu = {"value": v, "unit": "FFIs/s", "cores": cores, "kind": "port",
+				"sample": f"first {ns} FFIs of the benchmark cube, oracle restatement (numpy/scipy), spawn Pool({cores}).imap, {dt:.1f} s"}
+		except Exception as err:  # the baseline must never take the bench line down
+			cpu = {"value": None, "unit": "FFIs/s", "cores": cores, "kind": "port", "sample": f"failed: {err!r}"}
+
+	line = {
+		"metric": "FFIs/sec background-fitted (2048x2048)", "value": value, "unit": "FFIs/s", "n_gpus": world,
+		"steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+		"scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+		"config": {"workload": "synthetic single CCD 2048x2048 x 1,340 FFIs (30-min cadence sector), TESS path camera 1 ccd 2, 3 rounds",
+			"ffis_per_gpu": n, "ffis_per_launch": chunk, "l2": "inputs (22.5 GB/GPU) larger than L2", "parallelism": f"cadence shards x{world}"},
+		"roofline": roofline, "cpu_baseline": cpu,
+		"e2e": {"value": e2e_value, "unit": "FFIs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+			"note": f"pinned host sample of {ne} FFIs cycled {reps}x per step; results (bkg f32 + mask u8) copied back"},
+		"gpu_launches": launches, "clocks": clocks,
+		"kernel_ms": {k: round(v, 3) for k, v in prof.items()}, "prepare_path": prep,
+	}
+	print(json.dumps(line), flush=True)
+	if world > 1:
+		dist.destroy_process_group()
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument('--gpus', type=int, default=1)
+	ap.add_argument('--steps', type=int, default=3)
+	ap.add_argument('--warmup', type=int, default=3)
+	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+	ap.add_argument('--ffis', type=int, default=1340, help='FFIs per GPU per step')
+	ap.add_argument('--chunk', type=int, default=16, help='FFIs per tbk_fit_batch launch')
+	ap.add_argument('--e2e-ffis', type=int, default=128, help='pinned host sample size for the end-to-end leg')
+	ap.add_argument('--prepare-ffis', type=int, default=256)
+	ap.add_argument('--no-prepare', dest='prepare', action='store_false')
+	ap.add_argument('--no-cpu', action='store_true')
+	ap.add_argument('--ref-ffis', type=int, default=None)
+	args = ap.parse_args()
+	if args.impl == 'reference':
+		run_reference(args)
+	else:
+		run_b200(args)
+
+
+if __name__ == '__main__':
+	main()

@@ -133,6 +133,29 @@ int tbk_sum_finalize(tbk_plan* plan, const double* sum, const int32_t* nimg, con
 int tbk_debug_fetch(tbk_plan* plan, const void* workspace, int B, int b, int round,
 	double* s2, double* mesh);
 
+/* Kernel classes reported by tbk_fit_batch_profiled (milliseconds per class, summed over rounds). */
+enum {
+	TBK_K_TILE_BASE = 0,   /* mask build + sigma-clipped statistics of every mesh */
+	TBK_K_TILE_ROUND,      /* sigma-clipped statistics of the meshes that see the radial gradient */
+	TBK_K_ZP_MIN,          /* zeropoint pass of rounds >= 2 */
+	TBK_K_RING_GATHER,     /* ring sample gather + log10 */
+	TBK_K_RING_KDE,        /* KDE mode per ring */
+	TBK_K_RADIAL_FIT,      /* moving median + spline */
+	TBK_K_MESH,            /* mesh estimator, IDW, 3x3 median, prefilter */
+	TBK_K_FINAL,           /* mesh-to-pixel interpolation + radial + write */
+	TBK_K_MISC,            /* per-FFI bookkeeping kernels */
+	TBK_K_COUNT
+};
+
+/* Same as tbk_fit_batch, but synchronises the stream and returns the device time of every kernel
+ * class in ms[TBK_K_COUNT] (CUDA events between launches).  For measurement only. */
+int tbk_fit_batch_profiled(tbk_plan* plan, const float* cube, int B, const tbk_ffi_meta* meta,
+	const uint8_t* extra_mask, float* bkg_out, uint8_t* mask_out, tbk_ffi_status* status,
+	void* workspace, void* stream, float* ms);
+
+/* Number of kernels this library has launched in this process so far. */
+unsigned long long tbk_launch_count(void);
+
 /* Byte offsets of the workspace sections for a batch of B (diagnostics / tests):
  * offsets[0..7] = ctl, tile_base, tile_nf, coef, mesh_hist, s2_raw, s2_hist, ring_v;
  * sizes[0..2] = sizeof(FfiCtl), sizeof(TileStat), number of non-flat tiles. */

@@ -6,6 +6,6 @@ the sumimage accumulation.  Host side: Python + a C-ABI CUDA library (include/tb
 from .backgrounds import fit_background, BackgroundFitter, make_meta, meta_from_headers  # noqa: F401
 from .io import FFIImage  # noqa: F401
 from .quality import TESSQualityFlags, PixelQualityFlags  # noqa: F401
-from .prepare import prepare_stack, SectorResult  # noqa: F401
+from .prepare import prepare_stack, fit_stack_host, SectorResult  # noqa: F401
 
 __version__ = '0.1.0'

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(_HERE, 'lib', 'libtbk.so')
 
 TBK_MAX_ROUNDS = 8
+KERNEL_CLASSES = ('tile_base', 'tile_round', 'zp_min', 'ring_gather', 'ring_kde', 'radial_fit', 'mesh', 'final', 'misc')
 
 
 class TbkError(RuntimeError):
@@ -47,6 +48,8 @@ SIGNATURES = {
 	'tbk_sum_accumulate': (C.c_int, [_p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p]),
 	'tbk_sum_finalize': (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_double, _p, _p, _p]),
 	'tbk_debug_fetch': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
+	'tbk_fit_batch_profiled': (C.c_int, [_p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.POINTER(C.c_float)]),
+	'tbk_launch_count': (C.c_ulonglong, []),
 	'tbk_workspace_layout': (C.c_int, [_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 	'tbk_last_error': (C.c_char_p, []),
 	'tbk_version': (C.c_int, []),

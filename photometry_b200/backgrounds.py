@@ -100,7 +100,7 @@ class BackgroundFitter:
 		meta = np.ascontiguousarray(meta, dtype=META_DTYPE)
 		return torch.from_numpy(meta.view(np.uint8).copy()).to(self.device, non_blocking=True)
 
-	def fit(self, cube, meta=None, extra_mask=None, bkg_out=None, mask_out=None, status_out=None):
+	def fit(self, cube, meta=None, extra_mask=None, bkg_out=None, mask_out=None, status_out=None, profile=None):
 		"""
 		Fit a device-resident batch.  ``cube`` float32 cuda tensor [B, H, W]; ``meta`` a
 		``tbk_ffi_meta`` numpy array or an already uploaded uint8 tensor; ``extra_mask`` optional
@@ -126,8 +126,16 @@ class BackgroundFitter:
 		status = status_out if status_out is not None else torch.empty(B * STATUS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
 		ws = self.workspace(B)
 		stream = torch.cuda.current_stream(self.device).cuda_stream
-		check(self.lib.tbk_fit_batch(self._plan, _ptr(cube), B, _ptr(meta_d), _ptr(extra_mask), _ptr(bkg),
-			_ptr(mask), _ptr(status), _ptr(ws), C.c_void_p(stream)), 'tbk_fit_batch')
+		if profile is not None:
+			# measurement aid: synchronising variant that returns ms per kernel class in ``profile`` (dict)
+			ms = (C.c_float * len(_lib.KERNEL_CLASSES))()
+			check(self.lib.tbk_fit_batch_profiled(self._plan, _ptr(cube), B, _ptr(meta_d), _ptr(extra_mask), _ptr(bkg),
+				_ptr(mask), _ptr(status), _ptr(ws), C.c_void_p(stream), ms), 'tbk_fit_batch_profiled')
+			for name, v in zip(_lib.KERNEL_CLASSES, ms):
+				profile[name] = profile.get(name, 0.0) + float(v)
+		else:
+			check(self.lib.tbk_fit_batch(self._plan, _ptr(cube), B, _ptr(meta_d), _ptr(extra_mask), _ptr(bkg),
+				_ptr(mask), _ptr(status), _ptr(ws), C.c_void_p(stream)), 'tbk_fit_batch')
 		self._last = (ws, B)
 		return bkg, mask, status
 

@@ -251,8 +251,19 @@ extern "C" int tbk_fit_batch(tbk_plan* p, const float* cube, int B, const tbk_ff
 		return TBK_ERR_INVALID;
 	}
 	Workspace ws = carve(p, workspace, B);
-	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, nullptr);
 }
+
+extern "C" int tbk_fit_batch_profiled(tbk_plan* p, const float* cube, int B, const tbk_ffi_meta* meta,
+	const uint8_t* extra_mask, float* bkg_out, uint8_t* mask_out, tbk_ffi_status* status,
+	void* workspace, void* stream, float* ms)
+{
+	if (!p || !cube || !bkg_out || !mask_out || !workspace || !ms || B <= 0) { tbk_set_error("tbk_fit_batch_profiled: NULL argument or B <= 0"); return TBK_ERR_INVALID; }
+	Workspace ws = carve(p, workspace, B);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, ms);
+}
+
+extern "C" unsigned long long tbk_launch_count(void) { return tbk_launch_counter(); }
 
 extern "C" int tbk_time_smooth(tbk_plan* p, const float* bkg, int n, int w,
 	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi, float* out, void* stream)

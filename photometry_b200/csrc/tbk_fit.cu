@@ -700,34 +700,63 @@ static inline bool launch_ok(const char* what)
 	return true;
 }
 
+// Optional per-kernel-class timing: events are recorded between launches and read back afterwards.
+struct FitProf {
+	cudaEvent_t ev[128];
+	int cls[128];
+	int n;
+};
+static unsigned long long g_launches = 0;
+unsigned long long tbk_launch_counter(void) { return g_launches; }
+
+#define LAUNCH(cls_, ...) do { __VA_ARGS__; ++g_launches; if (prof) { cudaEventRecord(prof->ev[prof->n + 1], st); prof->cls[prof->n] = (cls_); ++prof->n; } } while (0)
+
 int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
 	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
-	tbk_ffi_status* status, cudaStream_t st)
+	tbk_ffi_status* status, cudaStream_t st, float* prof_ms)
 {
+	FitProf* prof = nullptr;
+	FitProf pstore;
+	if (prof_ms) {
+		prof = &pstore; prof->n = 0;
+		for (int i = 0; i < 128; ++i) cudaEventCreate(&prof->ev[i]);
+		cudaEventRecord(prof->ev[0], st);
+	}
 	const dim3 gt(P.ntiles, B);
 	const int gb = (B + 127) / 128;
-	k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B);
-	k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask);
-	k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B);
+	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
+	LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
+	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));
 	if (!launch_ok("base")) return TBK_ERR_CUDA;
 	const size_t mesh_smem = 3 * (size_t)P.ntiles * sizeof(double);
 	for (int round = 0; round < P.bkgiters; ++round) {
 		if (P.use_radial) {
 			if (round > 0) {
-				k_zp_min<<<gt, TBK_NT, 0, st>>>(P, ws, cube, mask);
-				k_set_zp<<<gb, 128, 0, st>>>(ws, B);
+				LAUNCH(TBK_K_ZP_MIN, (k_zp_min<<<gt, TBK_NT, 0, st>>>(P, ws, cube, mask)));
+				LAUNCH(TBK_K_MISC, (k_set_zp<<<gb, 128, 0, st>>>(ws, B)));
 			}
-			k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round);
-			k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws);
-			k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B);
+			LAUNCH(TBK_K_RING_GATHER, (k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round)));
+			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
+			LAUNCH(TBK_K_RADIAL_FIT, (k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B)));
 			if (P.n_nonflat > 0)
-				k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask);
+				LAUNCH(TBK_K_TILE_ROUND, (k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask)));
 		}
-		k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round);
+		LAUNCH(TBK_K_MESH, (k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round)));
 		if (!launch_ok("round")) return TBK_ERR_CUDA;
 	}
-	k_final<<<gt, TBK_NT, 0, st>>>(P, ws, bkg, mask);
+	LAUNCH(TBK_K_FINAL, (k_final<<<gt, TBK_NT, 0, st>>>(P, ws, bkg, mask)));
 	if (!launch_ok("final")) return TBK_ERR_CUDA;
+	if (prof) {
+		cudaError_t e = cudaStreamSynchronize(st);
+		for (int i = 0; i < TBK_K_COUNT; ++i) prof_ms[i] = 0.f;
+		for (int i = 0; i < prof->n; ++i) {
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, prof->ev[i], prof->ev[i + 1]);
+			prof_ms[prof->cls[i]] += ms;
+		}
+		for (int i = 0; i < 128; ++i) cudaEventDestroy(prof->ev[i]);
+		if (e != cudaSuccess) { tbk_set_error("profiled fit: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	}
 	return TBK_OK;
 }
 

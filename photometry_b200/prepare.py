@@ -116,3 +116,50 @@ def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, k
 		sumimage, pixels_used = fitter.sum_finalize(sum_, nimg, used, numfiles, backgrounds_pixels_threshold)
 	return SectorResult(bkg_us, bkg, flags, images, sumimage, pixels_used, nimg, used,
 		status.cpu().numpy().view(STATUS_DTYPE), numfiles)
+
+
+def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3, extra_mask=None):
+	"""
+	End-to-end ``fit_background`` over a HOST-resident stack (the pool loop of prepare.py:291 with the
+	FFIs already decoded): pinned host cube -> device -> fit -> pinned host results, pipelined over
+	``nbuf`` device staging buffers and three streams (H2D, compute, D2H).
+
+	host_cube  float32 pinned CPU tensor [n, H, W];  out_bkg float32 / out_mask uint8 pinned CPU tensors
+	Returns the number of bytes copied (h2d, d2h).
+	"""
+	n, H, W = host_cube.shape
+	dev = fitter.device
+	meta_d = fitter.meta_to_device(np.ascontiguousarray(meta))
+	isz = meta.dtype.itemsize
+	s_in, s_c, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+	ins = [torch.empty((chunk, H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+	bks = [torch.empty((chunk, H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+	mks = [torch.empty((chunk, H, W), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+	ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+	ev_c = [torch.cuda.Event() for _ in range(nbuf)]
+	ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+	cur = torch.cuda.current_stream(dev)
+	for s in (s_in, s_c, s_out):
+		s.wait_stream(cur)
+	for idx, a in enumerate(range(0, n, chunk)):
+		b = min(a + chunk, n)
+		m = b - a
+		k = idx % nbuf
+		if idx >= nbuf:
+			s_in.wait_event(ev_c[k])     # staging input free once its fit has run
+			s_c.wait_event(ev_out[k])    # result buffers free once copied out
+		with torch.cuda.stream(s_in):
+			ins[k][:m].copy_(host_cube[a:b], non_blocking=True)
+			ev_in[k].record(s_in)
+		s_c.wait_event(ev_in[k])
+		with torch.cuda.stream(s_c):
+			fitter.fit(ins[k][:m], meta_d[a * isz:b * isz], bkg_out=bks[k][:m], mask_out=mks[k][:m])
+			ev_c[k].record(s_c)
+		s_out.wait_event(ev_c[k])
+		with torch.cuda.stream(s_out):
+			out_bkg[a:b].copy_(bks[k][:m], non_blocking=True)
+			out_mask[a:b].copy_(mks[k][:m], non_blocking=True)
+			ev_out[k].record(s_out)
+	for s in (s_in, s_c, s_out):
+		cur.wait_stream(s)
+	return n * H * W * 4, n * H * W * 5
