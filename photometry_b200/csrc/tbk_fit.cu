@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(TBK_NT) k_zp_min(PlanDev P, Workspace ws,
 	if (c.all_masked || c.no_good_mesh) return;
 	const int ty = tile / P.nx, tx = tile % P.nx;
 	zoom_tile_load(z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
+	zoom_tile_stage(z, c, P.zoom_w);
 	__syncthreads();
 	const size_t img = (size_t)b * P.H * P.W;
 	const int lcol = tile_lcol(tid);
@@ -150,11 +151,11 @@ __global__ void __launch_bounds__(TBK_NT) k_zp_min(PlanDev P, Workspace ws,
 		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
 		const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + off));
 		double sq[4];
-		zoom_eval4(z, P.zoom_w, lrow, lcol, sq);
-		if (!m.x) mn = fmin(mn, (double)x.x - zoom_clip(c, sq[0]));
-		if (!m.y) mn = fmin(mn, (double)x.y - zoom_clip(c, sq[1]));
-		if (!m.z) mn = fmin(mn, (double)x.z - zoom_clip(c, sq[2]));
-		if (!m.w) mn = fmin(mn, (double)x.w - zoom_clip(c, sq[3]));
+		zoom_eval4(z, z.w, lrow, lcol, sq);
+		if (!m.x) mn = fmin(mn, (double)x.x - zoom_clip_s(z, sq[0]));
+		if (!m.y) mn = fmin(mn, (double)x.y - zoom_clip_s(z, sq[1]));
+		if (!m.z) mn = fmin(mn, (double)x.z - zoom_clip_s(z, sq[2]));
+		if (!m.w) mn = fmin(mn, (double)x.w - zoom_clip_s(z, sq[3]));
 	}
 	block_sum_min_max(red, cnt, mn, mx);
 	if (tid == 0 && mn < INFINITY) atomicMin(&c.min_key, dkey(mn));
@@ -672,20 +673,21 @@ __global__ void __launch_bounds__(TBK_NT) k_final(PlanDev P, Workspace ws,
 		return;
 	}
 	zoom_tile_load(z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
+	zoom_tile_stage(z, c, P.zoom_w);
 	__syncthreads();
-	const bool nonflat = P.use_radial && c.radial_ok && P.tile_slot[tile] >= 0;
-	const double cflat = (P.use_radial && c.radial_ok) ? c.c_flat : 0.0;
+	const bool nonflat = P.use_radial && z.radial_ok && P.tile_slot[tile] >= 0;
+	const double cflat = (P.use_radial && z.radial_ok) ? z.c_flat : 0.0;
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		const int lrow = tile_lrow(tid, j);
 		const int gy = ty * TBK_TILE + lrow;
 		double sq[4];
-		zoom_eval4(z, P.zoom_w, lrow, lcol, sq);
+		zoom_eval4(z, z.w, lrow, lcol, sq);
 		float o[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			const double rad = nonflat ? radial_value(c, P, pixel_radius(P, gy, gx + q)) : cflat;
-			o[q] = (float)(rad + zoom_clip(c, sq[q]));
+			o[q] = (float)(rad + zoom_clip_s(z, sq[q]));
 		}
 		const size_t off = img + (size_t)gy * P.W + gx;
 		*reinterpret_cast<float4*>(bkg + off) = make_float4(o[0], o[1], o[2], o[3]);

@@ -20,6 +20,9 @@ __device__ __forceinline__ int reflect_fold(int i, int n)
 // 5x5 neighbourhood of prefiltered coefficients around tile (ty, tx), rows/cols ty-2 .. ty+2.
 struct ZoomTile {
 	double c[5][5];
+	double w[64 * 4];          // zoom weights staged from global (one LDS instead of an LDG per tap)
+	double mesh_min, mesh_max, c_flat;
+	int mesh_const, radial_ok;
 };
 
 __device__ __forceinline__ void zoom_tile_load(ZoomTile& z, const double* __restrict__ coef,
@@ -30,6 +33,21 @@ __device__ __forceinline__ void zoom_tile_load(ZoomTile& z, const double* __rest
 		int a = i / 5, b = i % 5;
 		z.c[a][b] = coef[reflect_fold(ty - 2 + a, ny) * nx + reflect_fold(tx - 2 + b, nx)];
 	}
+}
+
+__device__ __forceinline__ void zoom_tile_stage(ZoomTile& z, const FfiCtl& c, const double* __restrict__ zw)
+{
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) z.w[i] = __ldg(zw + i);
+	if (threadIdx.x == 0) {
+		z.mesh_min = c.mesh_min; z.mesh_max = c.mesh_max; z.mesh_const = c.mesh_const;
+		z.radial_ok = c.radial_ok; z.c_flat = c.c_flat;
+	}
+}
+
+__device__ __forceinline__ double zoom_clip_s(const ZoomTile& z, double v)
+{
+	if (z.mesh_const) return z.mesh_min;
+	return fmin(fmax(v, z.mesh_min), z.mesh_max);
 }
 
 // Interpolated (unclipped) mesh value at tile-local pixel (lrow, lcol).
