@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -30,6 +31,7 @@ struct tbk_plan {
 	std::vector<void*> allocs;
 	int* zero_flags;
 	int zero_cap;
+	int tile_kernel;   // 0: CTA-per-mesh generic kernel, 1: warp-per-mesh register kernel (default)
 	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv;
 };
 
@@ -131,6 +133,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
 	p->zero_flags = nullptr; p->zero_cap = 0;
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = (tk && tk[0] == '0') ? 0 : 1; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;
@@ -251,7 +254,7 @@ extern "C" int tbk_fit_batch(tbk_plan* p, const float* cube, int B, const tbk_ff
 		return TBK_ERR_INVALID;
 	}
 	Workspace ws = carve(p, workspace, B);
-	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, nullptr);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, nullptr, p->tile_kernel);
 }
 
 extern "C" int tbk_fit_batch_profiled(tbk_plan* p, const float* cube, int B, const tbk_ffi_meta* meta,
@@ -260,7 +263,7 @@ extern "C" int tbk_fit_batch_profiled(tbk_plan* p, const float* cube, int B, con
 {
 	if (!p || !cube || !bkg_out || !mask_out || !workspace || !ms || B <= 0) { tbk_set_error("tbk_fit_batch_profiled: NULL argument or B <= 0"); return TBK_ERR_INVALID; }
 	Workspace ws = carve(p, workspace, B);
-	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, ms);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, ms, p->tile_kernel);
 }
 
 extern "C" unsigned long long tbk_launch_count(void) { return tbk_launch_counter(); }

@@ -1,6 +1,7 @@
 // tbk_fit.cu -- kernels of the batched fit_background path (photometry/backgrounds.py:86-211).
 #include "tbk_common.cuh"
 #include "tbk_tile.cuh"
+#include "tbk_tile_warp.cuh"
 #include "tbk_zoom.cuh"
 #include "tbk_internal.h"
 
@@ -103,6 +104,62 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_base(PlanDev P, Workspace ws,
 	if (nonflat) return;
 	TileStat st = tile_sigma_clip<float>(v, valid, sm);
 	if (tid == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+}
+
+// K_tile_base_warp: same outputs as k_tile_base, one warp (= one CTA of 32 threads) per mesh, pixels in registers.
+// Lane l, load i (0..31) owns row 2i + l/16, columns 4(l%16) .. +3: every warp load covers two 256 B row segments.
+__global__ void __launch_bounds__(32) k_tile_base_warp(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
+{
+	__shared__ TileWarpSmem sm;
+	const int tile = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	FfiCtl& c = ws.ctl[b];
+	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
+	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + (lane >> 4)) * P.W + gx;
+	const bool excl = (c.mars && gx >= 1536) || c.earth;
+	const float cutoff = P.flux_cutoff;
+
+	float v[128];
+#pragma unroll
+	for (int i = 0; i < 32; ++i) {
+		const float4 r = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(2 * i) * P.W));
+		v[4 * i] = r.x; v[4 * i + 1] = r.y; v[4 * i + 2] = r.z; v[4 * i + 3] = r.w;
+	}
+	bool nonzero = false;
+	int n = 0;
+	float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+	for (int i = 0; i < 32; ++i) {
+		const size_t off = base + (size_t)(2 * i) * P.W;
+		uchar4 ex = make_uchar4(0, 0, 0, 0);
+		if (extra) ex = __ldg(reinterpret_cast<const uchar4*>(extra + off));
+		const unsigned char e4[4] = {ex.x, ex.y, ex.z, ex.w};
+		unsigned char m4[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const float x = v[4 * i + q];
+			nonzero |= !(x == 0.0f);
+			const bool ok = (x >= 0.0f) && (x <= cutoff) && !excl && !e4[q];
+			m4[q] = ok ? 0 : 1;
+			n += ok ? 1 : 0;
+			const float xv = x + 0.0f;  // -0.0 -> +0.0
+			mn = fminf(mn, ok ? xv : INFINITY);
+			mx = fmaxf(mx, ok ? xv : -INFINITY);
+			v[4 * i + q] = ok ? xv : __uint_as_float(TW_INVALID);
+		}
+		*reinterpret_cast<uchar4*>(mask_out + off) = make_uchar4(m4[0], m4[1], m4[2], m4[3]);
+	}
+	n = warp_sum(n);
+	for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+	const bool any_nz = __any_sync(0xffffffffu, nonzero);
+	if (lane == 0) {
+		if (any_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+		if (n > 0) { atomicAdd(&c.n_valid, n); atomicMin(&c.min_bits, __float_as_uint(mn)); }
+	}
+	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
+	const TileStat st = tile_warp_stats(v, n, mn, mx, sm, lane);
+	if (lane == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
 
 // K_post_base: all-zero rule (pixel_flags.py:54-56), all-masked early-out (backgrounds.py:101-102),
@@ -715,7 +772,7 @@ unsigned long long tbk_launch_counter(void) { return g_launches; }
 
 int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
 	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
-	tbk_ffi_status* status, cudaStream_t st, float* prof_ms)
+	tbk_ffi_status* status, cudaStream_t st, float* prof_ms, int tile_kernel)
 {
 	FitProf* prof = nullptr;
 	FitProf pstore;
@@ -727,7 +784,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	const dim3 gt(P.ntiles, B);
 	const int gb = (B + 127) / 128;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
-	LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
+	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
+	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
 	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));
 	if (!launch_ok("base")) return TBK_ERR_CUDA;
 	const size_t mesh_smem = 3 * (size_t)P.ntiles * sizeof(double);

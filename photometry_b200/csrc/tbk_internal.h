@@ -12,7 +12,7 @@ void tbk_set_error(const char* fmt, ...);
 int tbk_fit_configure(void);
 int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
 	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
-	tbk_ffi_status* status, cudaStream_t st, float* prof_ms);
+	tbk_ffi_status* status, cudaStream_t st, float* prof_ms, int tile_kernel);
 unsigned long long tbk_launch_counter(void);
 
 // tbk_prepare.cu
