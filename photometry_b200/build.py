@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
 		return LIBPATH
 	os.makedirs(LIBDIR, exist_ok=True)
 	nvcc = os.environ.get('NVCC', 'nvcc')
-	cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIBPATH] + [os.path.join(CSRC, s) for s in SOURCES]
+	extra = os.environ.get('TBK_NVCC_FLAGS', '').split()
+	cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIBPATH] + [os.path.join(CSRC, s) for s in SOURCES]
 	res = subprocess.run(cmd, capture_output=True, text=True)
 	if res.returncode != 0:
 		raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

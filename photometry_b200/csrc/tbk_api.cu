@@ -32,7 +32,7 @@ struct tbk_plan {
 	int* zero_flags;
 	int zero_cap;
 	int tile_kernel;   // 0: CTA-per-mesh generic kernel, 1: warp-per-mesh register kernel (default)
-	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv;
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin;
 };
 
 // photometry/backgrounds.py:121-138
@@ -87,6 +87,7 @@ static void layout(tbk_plan* p, int B, size_t* total)
 	p->off_s2raw = o;  o = align_up(o + sizeof(double) * (size_t)B * std::max(P.nrings, 1));
 	p->off_s2hist = o; o = align_up(o + sizeof(double) * (size_t)B * P.bkgiters * std::max(P.nrings, 1));
 	p->off_ringv = o;  o = align_up(o + sizeof(double) * (size_t)B * std::max(P.nringpix, 1));
+	p->off_sbmin = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
 	*total = o;
 }
 
@@ -104,6 +105,7 @@ static Workspace carve(tbk_plan* p, void* base, int B)
 	ws.s2_raw = (double*)(b + p->off_s2raw);
 	ws.s2_hist = (double*)(b + p->off_s2hist);
 	ws.ring_v = (double*)(b + p->off_ringv);
+	ws.sbmin = (float*)(b + p->off_sbmin);
 	return ws;
 }
 

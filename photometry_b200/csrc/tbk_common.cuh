@@ -71,6 +71,7 @@ struct Workspace {
 	double* s2_raw;         // [B][nrings] ring modes of the current round
 	double* s2_hist;        // [B][rounds][nrings] smoothed ring values per round (diagnostics)
 	double* ring_v;         // [B][nringpix] ring samples (NaN = masked)
+	float* sbmin;           // [B][ntiles][64] minimum valid pixel of every 8x8 sub-block (+inf = none)
 };
 
 // ---------------------------------------------------------------------------------------------

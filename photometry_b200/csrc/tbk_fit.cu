@@ -108,7 +108,12 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_base(PlanDev P, Workspace ws,
 
 // K_tile_base_warp: same outputs as k_tile_base, one warp (= one CTA of 32 threads) per mesh, pixels in registers.
 // Lane l, load i (0..31) owns row 2i + l/16, columns 4(l%16) .. +3: every warp load covers two 256 B row segments.
-__global__ void __launch_bounds__(32) k_tile_base_warp(PlanDev P, Workspace ws,
+// Also records the minimum valid pixel of every 8x8 sub-block (ws.sbmin) for the pruned zeropoint pass.
+#ifndef TW_MINB
+#define TW_MINB 1
+#endif
+template <bool HAS_EXTRA>
+__global__ void __launch_bounds__(32, TW_MINB) k_tile_base_warp(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
 {
 	__shared__ TileWarpSmem sm;
@@ -117,48 +122,72 @@ __global__ void __launch_bounds__(32) k_tile_base_warp(PlanDev P, Workspace ws,
 	FfiCtl& c = ws.ctl[b];
 	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
 	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + (lane >> 4)) * P.W + gx;
-	const bool excl = (c.mars && gx >= 1536) || c.earth;
-	const float cutoff = P.flux_cutoff;
+	const size_t step = (size_t)2 * P.W;
+	// manual excludes are mesh-uniform: the Mars boundary (column 1536) is a multiple of the mesh size
+	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
+	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
 
-	float v[128];
+	uint32_t v[128];
+	{
+		const float* p = cube + base;
 #pragma unroll
-	for (int i = 0; i < 32; ++i) {
-		const float4 r = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(2 * i) * P.W));
-		v[4 * i] = r.x; v[4 * i + 1] = r.y; v[4 * i + 2] = r.z; v[4 * i + 3] = r.w;
+		for (int i = 0; i < 32; ++i) {
+			const float4 r = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * step));
+			// x + 0.0f maps -0.0 to +0.0; non-negative finite floats then order like unsigned integers,
+			// negative / NaN / inf bit patterns all compare above the cutoff
+			v[4 * i] = __float_as_uint(r.x + 0.0f); v[4 * i + 1] = __float_as_uint(r.y + 0.0f);
+			v[4 * i + 2] = __float_as_uint(r.z + 0.0f); v[4 * i + 3] = __float_as_uint(r.w + 0.0f);
+		}
 	}
-	bool nonzero = false;
-	int n = 0;
-	float mn = INFINITY, mx = -INFINITY;
+	uint32_t nz = 0u, sb[8];
+	int nbad = 0;
+#pragma unroll
+	for (int a = 0; a < 8; ++a) sb[a] = TW_INVALID;
 #pragma unroll
 	for (int i = 0; i < 32; ++i) {
-		const size_t off = base + (size_t)(2 * i) * P.W;
-		uchar4 ex = make_uchar4(0, 0, 0, 0);
-		if (extra) ex = __ldg(reinterpret_cast<const uchar4*>(extra + off));
-		const unsigned char e4[4] = {ex.x, ex.y, ex.z, ex.w};
-		unsigned char m4[4];
+		const size_t off = base + (size_t)i * step;
+		uint32_t ex = 0u;
+		if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
+		uint32_t m = 0u;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const float x = v[4 * i + q];
-			nonzero |= !(x == 0.0f);
-			const bool ok = (x >= 0.0f) && (x <= cutoff) && !excl && !e4[q];
-			m4[q] = ok ? 0 : 1;
-			n += ok ? 1 : 0;
-			const float xv = x + 0.0f;  // -0.0 -> +0.0
-			mn = fminf(mn, ok ? xv : INFINITY);
-			mx = fmaxf(mx, ok ? xv : -INFINITY);
-			v[4 * i + q] = ok ? xv : __uint_as_float(TW_INVALID);
+			const uint32_t k = v[4 * i + q];
+			nz |= k;
+			bool ok = k <= cut;
+			if (excl) ok = false;
+			if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
+			m |= ok ? 0u : (1u << (8 * q));
+			const uint32_t kv = ok ? k : TW_INVALID;
+			v[4 * i + q] = kv;
+			sb[i >> 2] = min(sb[i >> 2], kv);
 		}
-		*reinterpret_cast<uchar4*>(mask_out + off) = make_uchar4(m4[0], m4[1], m4[2], m4[3]);
+		nbad += __popc(m);
+		*reinterpret_cast<unsigned int*>(mask_out + off) = m;
 	}
-	n = warp_sum(n);
-	for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-	const bool any_nz = __any_sync(0xffffffffu, nonzero);
+	// sub-block minima: rows 8a..8a+7 are loads 4a..4a+3; columns 8c..8c+7 are lanes {2c, 2c+1} + {0, 16}
+	uint32_t kmin = TW_INVALID;
+#pragma unroll
+	for (int a = 0; a < 8; ++a) {
+		uint32_t t = sb[a];
+		t = min(t, __shfl_xor_sync(0xffffffffu, t, 1));
+		t = min(t, __shfl_xor_sync(0xffffffffu, t, 16));
+		sb[a] = t;
+		kmin = min(kmin, t);
+	}
+	if ((lane & 17) == 0) {
+		float* dst = ws.sbmin + ((size_t)b * P.ntiles + tile) * 64 + (lane >> 1);
+#pragma unroll
+		for (int a = 0; a < 8; ++a) dst[a * 8] = __uint_as_float(sb[a]);
+	}
+	kmin = __reduce_min_sync(0xffffffffu, kmin);
+	const int n = 4096 - __reduce_add_sync(0xffffffffu, nbad);
+	nz = __reduce_or_sync(0xffffffffu, nz);
 	if (lane == 0) {
-		if (any_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
-		if (n > 0) { atomicAdd(&c.n_valid, n); atomicMin(&c.min_bits, __float_as_uint(mn)); }
+		if (nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+		if (n > 0) { atomicAdd(&c.n_valid, n); atomicMin(&c.min_bits, kmin); }
 	}
 	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
-	const TileStat st = tile_warp_stats(v, n, mn, mx, sm, lane);
+	const TileStat st = tile_warp_stats(v, n, kmin, sm, lane);
 	if (lane == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
 
@@ -785,7 +814,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	const int gb = (B + 127) / 128;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
 	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
-	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<true><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
+	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<false><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
 	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));
 	if (!launch_ok("base")) return TBK_ERR_CUDA;
 	const size_t mesh_smem = 3 * (size_t)P.ntiles * sizeof(double);
