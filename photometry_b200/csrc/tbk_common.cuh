@@ -52,6 +52,7 @@ struct FfiCtl {
 	int npts;                   // spline knots
 	int mesh_const;             // ptp(mesh) == 0
 	unsigned long long min_key; // rounds >= 2: ordered key of min(x - sq)
+	unsigned long long min_ub;  // rounds >= 2: ordered key of an upper bound of that minimum (pruning)
 	double zp;                  // zeropoint of the current round
 	double c_flat;              // radial value for r <= x0 (10**y0 - zp), 0 when !radial_ok
 	double x0, xlast;           // spline abscissa range (ext=3 clamp)

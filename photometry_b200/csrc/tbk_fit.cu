@@ -21,6 +21,7 @@ __global__ void k_init_ctl(PlanDev P, Workspace ws, const tbk_ffi_meta* __restri
 	c.npts = 0;
 	c.mesh_const = 0;
 	c.min_key = ~0ULL;
+	c.min_ub = ~0ULL;
 	c.zp = 0.0; c.c_flat = 0.0; c.x0 = 0.0; c.xlast = 0.0;
 	c.mesh_min = 0.0; c.mesh_max = 0.0;
 	int mars = 0, earth = 0;
@@ -247,6 +248,92 @@ __global__ void __launch_bounds__(TBK_NT) k_zp_min(PlanDev P, Workspace ws,
 	if (tid == 0 && mn < INFINITY) atomicMin(&c.min_key, dkey(mn));
 }
 
+// K_zp_bound / K_zp_exact: the same minimum without touching every pixel.  k_tile_base_warp left the
+// minimum valid pixel of every 8x8 sub-block in ws.sbmin.  Inside a mesh the interpolated background is
+// Lipschitz: |sq(p) - sq(p0)| <= (Gx |dx| + Gy |dy|) / 64 with Gx, Gy the largest differences of adjacent
+// spline coefficients in the 5x5 neighbourhood (the derivative of a cubic B-spline surface is a convex
+// combination of coefficient differences; the clip to [mesh_min, mesh_max] is 1-Lipschitz).  So with
+// sq0 = sq(sub-block pixel (4,4)) and slack = 4 (Gx + Gy) / 64:
+//     xmin - (sq0 + slack)  <=  min over the sub-block of (x - sq)  <=  xmin - (sq0 - slack).
+// Pass 1 takes the smallest upper bound over the FFI; pass 2 evaluates exactly only the sub-blocks whose
+// lower bound does not exceed it -- the true minimiser is always among them.
+__device__ __forceinline__ double sm_max_bound(const FfiCtl& c) { return c.mesh_max; }
+
+struct ZpSmem {
+	ZoomTile z;
+	RedSmem red;
+	double slack;
+};
+
+__device__ __forceinline__ void zp_setup(ZpSmem& sm, const PlanDev& P, const Workspace& ws, const FfiCtl& c, int tile, int b)
+{
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	zoom_tile_load(sm.z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
+	zoom_tile_stage(sm.z, c, P.zoom_w);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double gx = 0.0, gy = 0.0;
+		for (int r = 0; r < 5; ++r) for (int k = 0; k < 4; ++k) {
+			gx = fmax(gx, fabs(sm.z.c[r][k + 1] - sm.z.c[r][k]));
+			gy = fmax(gy, fabs(sm.z.c[k + 1][r] - sm.z.c[k][r]));
+		}
+		sm.slack = sm.z.mesh_const ? 0.0 : (4.0 * (gx + gy) / 64.0) * (1.0 + 1e-9) + 1e-9;
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(64) k_zp_bound(PlanDev P, Workspace ws)
+{
+	__shared__ ZpSmem sm;
+	const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	zp_setup(sm, P, ws, c, tile, b);
+	const float xmin = ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + t];
+	double ub = INFINITY, dmy = 0.0; int cnt = 0;
+	if (xmin < INFINITY) {
+		const double sq0 = zoom_clip_s(sm.z, zoom_eval(sm.z, sm.z.w, 8 * (t >> 3) + 4, 8 * (t & 7) + 4));
+		ub = (double)xmin - (sq0 - sm.slack);
+	}
+	block_sum_min_max(sm.red, cnt, ub, dmy);
+	if (t == 0 && ub < INFINITY) atomicMin(&c.min_ub, dkey(ub));
+}
+
+__global__ void __launch_bounds__(64) k_zp_exact(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
+{
+	__shared__ ZpSmem sm;
+	const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	// cheap reject of the whole mesh: its smallest pixel against the coarsest bound
+	const float xmin = ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + t];
+	const double U = dkey_inv(c.min_ub);
+	if (__syncthreads_and(!((double)xmin - sm_max_bound(c) <= U))) return;
+	zp_setup(sm, P, ws, c, tile, b);
+	double mn = INFINITY;
+	if (xmin < INFINITY) {
+		const int r0 = 8 * (t >> 3), c0 = 8 * (t & 7);
+		const double sq0 = zoom_clip_s(sm.z, zoom_eval(sm.z, sm.z.w, r0 + 4, c0 + 4));
+		if ((double)xmin - (sq0 + sm.slack) <= U) {
+			const int ty = tile / P.nx, tx = tile % P.nx;
+			const size_t img = (size_t)b * P.H * P.W;
+			for (int i = 0; i < 8; ++i) {
+				const size_t off = img + (size_t)(ty * TBK_TILE + r0 + i) * P.W + tx * TBK_TILE + c0;
+				const float4 xa = __ldg(reinterpret_cast<const float4*>(cube + off)), xb = __ldg(reinterpret_cast<const float4*>(cube + off + 4));
+				const uchar4 ma = __ldg(reinterpret_cast<const uchar4*>(mask + off)), mb = __ldg(reinterpret_cast<const uchar4*>(mask + off + 4));
+				const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+				const unsigned char ms[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+				for (int j = 0; j < 8; ++j)
+					if (!ms[j]) mn = fmin(mn, (double)xs[j] - zoom_clip_s(sm.z, zoom_eval(sm.z, sm.z.w, r0 + i, c0 + j)));
+			}
+		}
+	}
+	double dmy = 0.0; int cnt = 0;
+	block_sum_min_max(sm.red, cnt, mn, dmy);
+	if (t == 0 && mn < INFINITY) atomicMin(&c.min_key, dkey(mn));
+}
+
 __global__ void k_set_zp(Workspace ws, int B)
 {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,6 +342,7 @@ __global__ void k_set_zp(Workspace ws, int B)
 	if (c.all_masked || c.no_good_mesh) return;
 	c.zp = 1.0 - dkey_inv(c.min_key);  // zeropoint = -min(pix) + 1.0
 	c.min_key = ~0ULL;
+	c.min_ub = ~0ULL;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -822,7 +910,11 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	for (int round = 0; round < P.bkgiters; ++round) {
 		if (P.use_radial) {
 			if (round > 0) {
-				LAUNCH(TBK_K_ZP_MIN, (k_zp_min<<<gt, TBK_NT, 0, st>>>(P, ws, cube, mask)));
+				if (tile_kernel == 0) LAUNCH(TBK_K_ZP_MIN, (k_zp_min<<<gt, TBK_NT, 0, st>>>(P, ws, cube, mask)));
+				else {
+					LAUNCH(TBK_K_ZP_MIN, (k_zp_bound<<<gt, 64, 0, st>>>(P, ws)));
+					LAUNCH(TBK_K_ZP_MIN, (k_zp_exact<<<gt, 64, 0, st>>>(P, ws, cube, mask)));
+				}
 				LAUNCH(TBK_K_MISC, (k_set_zp<<<gb, 128, 0, st>>>(ws, B)));
 			}
 			LAUNCH(TBK_K_RING_GATHER, (k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round)));
