@@ -27,7 +27,7 @@ extern "C" {
 #define TBK_VERSION 1
 #define TBK_TILE 64           /* Background2D box size, backgrounds.py:200 */
 #define TBK_MAX_ROUNDS 8      /* upper limit for bkgiters */
-#define TBK_MAX_RINGS 256     /* upper limit for the number of radial rings */
+#define TBK_MAX_RINGS 128     /* upper limit for the number of radial rings */
 
 typedef enum {
 	TBK_OK = 0,

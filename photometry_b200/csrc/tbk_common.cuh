@@ -59,6 +59,7 @@ struct FfiCtl {
 	double mesh_min, mesh_max;
 	double kx[TBK_MAX_RINGS];       // knot abscissae
 	double pp[TBK_MAX_RINGS][4];    // piecewise cubic: y = pp0 + s*(pp1 + s*(pp2 + s*pp3)), s = t - kx[i]
+	double seg[TBK_MAX_RINGS][5];   // dense table per ring-centre interval: {knot, pp0..pp3} of the covering piece
 	short seg_of_ring[TBK_MAX_RINGS]; // ring-centre interval -> spline piece
 };
 
@@ -130,6 +131,37 @@ __device__ __forceinline__ double radial_value(const FfiCtl& c, const PlanDev& P
 	double u = t - c.kx[s];
 	double y = c.pp[s][0] + u * (c.pp[s][1] + u * (c.pp[s][2] + u * c.pp[s][3]));
 	return exp10(y) - c.zp;
+}
+
+// Shared-memory copy of the per-FFI radial profile for kernels that evaluate it per pixel: the dense
+// ring-centre-interval table makes the piece lookup one multiply + one conversion (no search).
+struct RadialSmem2 {
+	double seg[TBK_MAX_RINGS][5];
+	double x0, xlast, c_flat, zp, center0, inv_step;
+	int radial_ok, nseg;
+};
+
+__device__ __forceinline__ void radial_stage(RadialSmem2& rs, const FfiCtl& c, const PlanDev& P)
+{
+	const int nseg = max(P.nrings - 1, 1);
+	for (int i = threadIdx.x; i < nseg * 5; i += blockDim.x) rs.seg[i / 5][i % 5] = c.seg[i / 5][i % 5];
+	if (threadIdx.x == 0) {
+		rs.x0 = c.x0; rs.xlast = c.xlast; rs.c_flat = c.c_flat; rs.zp = c.zp;
+		rs.center0 = ring_center(P, 0); rs.inv_step = 1.0 / P.step;
+		rs.radial_ok = c.radial_ok; rs.nseg = nseg;
+	}
+}
+
+__device__ __forceinline__ double radial_value_s(const RadialSmem2& rs, double r)
+{
+	if (!rs.radial_ok) return 0.0;
+	if (r <= rs.x0) return rs.c_flat;
+	const double t = fmin(r, rs.xlast);
+	const int i = max(0, min(rs.nseg - 1, (int)((t - rs.center0) * rs.inv_step)));
+	const double* e = rs.seg[i];
+	const double u = t - e[0];
+	const double y = e[1] + u * (e[2] + u * (e[3] + u * e[4]));
+	return exp10(y) - rs.zp;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -631,6 +631,8 @@ __global__ void k_radial_fit(PlanDev P, Workspace ws, tbk_ffi_status* status, in
 			const double cen = ring_center(P, i);
 			while (s + 1 < m - 1 && kx[s + 1] <= cen) ++s;
 			c.seg_of_ring[i] = (short)s;
+			c.seg[i][0] = kx[s];
+			for (int q = 0; q < 4; ++q) c.seg[i][1 + q] = c.pp[s][q];
 		}
 		c.x0 = kx[0]; c.xlast = kx[m - 1];
 		c.c_flat = exp10(ky[0]) - c.zp;
@@ -653,9 +655,12 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
 {
 	__shared__ TileSmem sm;
+	__shared__ RadialSmem2 rs;
 	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
 	const FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
+	radial_stage(rs, c, P);
+	__syncthreads();
 	const int tile = P.nonflat_tiles[slot];
 	const int ty = tile / P.nx, tx = tile % P.nx;
 	const size_t img = (size_t)b * P.H * P.W;
@@ -675,7 +680,7 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
 		for (int q = 0; q < 4; ++q) {
 			double d = 0.0;
 			if (!m4[q]) {
-				d = (double)x4[q] - radial_value(c, P, pixel_radius(P, gy, gx + q));
+				d = (double)x4[q] - radial_value_s(rs, pixel_radius(P, gy, gx + q));
 				valid |= 1u << (4 * j + q);
 			}
 			v[4 * j + q] = d;
@@ -830,6 +835,7 @@ __global__ void __launch_bounds__(TBK_NT) k_final(PlanDev P, Workspace ws,
 	float* __restrict__ bkg, uint8_t* __restrict__ mask_out)
 {
 	__shared__ ZoomTile z;
+	__shared__ RadialSmem2 rs;
 	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
 	const FfiCtl& c = ws.ctl[b];
 	const int ty = tile / P.nx, tx = tile % P.nx;
@@ -848,19 +854,22 @@ __global__ void __launch_bounds__(TBK_NT) k_final(PlanDev P, Workspace ws,
 	}
 	zoom_tile_load(z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
 	zoom_tile_stage(z, c, P.zoom_w);
+	const bool nonflat = P.use_radial && c.radial_ok && P.tile_slot[tile] >= 0;
+	if (nonflat) radial_stage(rs, c, P);
 	__syncthreads();
-	const bool nonflat = P.use_radial && z.radial_ok && P.tile_slot[tile] >= 0;
 	const double cflat = (P.use_radial && z.radial_ok) ? z.c_flat : 0.0;
+	ZoomCols zc;
+	zoom_cols_load(zc, z, lcol);
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		const int lrow = tile_lrow(tid, j);
 		const int gy = ty * TBK_TILE + lrow;
 		double sq[4];
-		zoom_eval4(z, z.w, lrow, lcol, sq);
+		zoom_cols_eval4(zc, z, lrow, sq);
 		float o[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const double rad = nonflat ? radial_value(c, P, pixel_radius(P, gy, gx + q)) : cflat;
+			const double rad = nonflat ? radial_value_s(rs, pixel_radius(P, gy, gx + q)) : cflat;
 			o[q] = (float)(rad + zoom_clip_s(z, sq[q]));
 		}
 		const size_t off = img + (size_t)gy * P.W + gx;

@@ -117,3 +117,39 @@ __device__ __forceinline__ double zoom_clip(const FfiCtl& c, double v)
 	if (c.mesh_const) return c.mesh_min;
 	return fmin(fmax(v, c.mesh_min), c.mesh_max);
 }
+
+// Register-resident evaluator for a thread that owns columns lcol .. lcol+3 in several rows of one mesh:
+// the column weights and the 5x4 coefficient block are loaded once; a row then costs 4 weight loads.
+struct ZoomCols {
+	double c[5][4];   // coefficient rows 0..4 of the neighbourhood, the 4 columns this half needs
+	double wx[4][4];  // column weights of the 4 pixels
+};
+
+__device__ __forceinline__ void zoom_cols_load(ZoomCols& zc, const ZoomTile& z, int lcol)
+{
+	const int ox = lcol >> 5;
+#pragma unroll
+	for (int a = 0; a < 5; ++a)
+#pragma unroll
+		for (int b = 0; b < 4; ++b) zc.c[a][b] = z.c[a][ox + b];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+#pragma unroll
+		for (int b = 0; b < 4; ++b) zc.wx[q][b] = z.w[4 * (lcol + q) + b];
+}
+
+__device__ __forceinline__ void zoom_cols_eval4(const ZoomCols& zc, const ZoomTile& z, int lrow, double (&out)[4])
+{
+	const double* wy = z.w + 4 * lrow;
+	const double w0 = wy[0], w1 = wy[1], w2 = wy[2], w3 = wy[3];
+	double r[4];
+	if (lrow < 32) {
+#pragma unroll
+		for (int b = 0; b < 4; ++b) r[b] = w0 * zc.c[0][b] + w1 * zc.c[1][b] + w2 * zc.c[2][b] + w3 * zc.c[3][b];
+	} else {
+#pragma unroll
+		for (int b = 0; b < 4; ++b) r[b] = w0 * zc.c[1][b] + w1 * zc.c[2][b] + w2 * zc.c[3][b] + w3 * zc.c[4][b];
+	}
+#pragma unroll
+	for (int q = 0; q < 4; ++q) out[q] = zc.wx[q][0] * r[0] + zc.wx[q][1] * r[1] + zc.wx[q][2] * r[2] + zc.wx[q][3] * r[3];
+}
