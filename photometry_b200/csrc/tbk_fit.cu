@@ -690,6 +690,42 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
 	if (tid == 0) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
 }
 
+// K_tile_round_w: same result as k_tile_round with the bucketed algorithm of tbk_tile_warp.cuh on float64
+// residuals.  128 threads per mesh; thread t, load i (0..7) owns row 8i + 2(t/32) + (t%32)/16, columns 4(t%16)..+3.
+__global__ void __launch_bounds__(128) k_tile_round_w(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
+{
+	__shared__ TileRound64Smem sm;
+	__shared__ RadialSmem2 rs;
+	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	radial_stage(rs, c, P);
+	__syncthreads();
+	const int tile = P.nonflat_tiles[slot];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	const int lane = tid & 31, w = tid >> 5;
+	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
+	unsigned long long key[32];
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		const int gy = ty * TBK_TILE + 8 * i + 2 * w + (lane >> 4);
+		const size_t off = (size_t)b * P.H * P.W + (size_t)gy * P.W + gx;
+		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
+		const unsigned int m = __ldg(reinterpret_cast<const unsigned int*>(mask + off));
+		const float x4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			unsigned long long k = ~0ULL;
+			if (!((m >> (8 * q)) & 0xFFu)) k = dkey((double)x4[q] - radial_value_s(rs, pixel_radius(P, gy, gx + q)));
+			key[4 * i + q] = k;
+		}
+	}
+	TileStat st; bool writer;
+	tile_block_stats64(key, sm, st, writer);
+	if (writer) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K_mesh_finalize: one CTA per FFI.  SExtractor estimator per mesh, mesh exclusion, IDW fill,
 // 3x3 nan-median, cubic-spline prefilter (photutils 1.3.0 Background2D).
@@ -930,7 +966,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
 			LAUNCH(TBK_K_RADIAL_FIT, (k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B)));
 			if (P.n_nonflat > 0)
-				LAUNCH(TBK_K_TILE_ROUND, (k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask)));
+				if (tile_kernel == 0) LAUNCH(TBK_K_TILE_ROUND, (k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask)));
+				else LAUNCH(TBK_K_TILE_ROUND, (k_tile_round_w<<<dim3(P.n_nonflat, B), 128, 0, st>>>(P, ws, cube, mask)));
 		}
 		LAUNCH(TBK_K_MESH, (k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round)));
 		if (!launch_ok("round")) return TBK_ERR_CUDA;

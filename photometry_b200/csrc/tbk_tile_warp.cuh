@@ -19,56 +19,112 @@
 
 #define TW_NB 2048
 #define TW_WORDS (TW_NB / 2)
-#define TW_INVALID 0x7f800000u   // +inf as key: masked pixel
+#define TW_INVALID 0x7f800000u   // +inf as key: masked pixel (float32 keys)
 
 // counter word w lives at w + (w >> 5): one pad word per 32 keeps the per-lane chunked scan (lane l owns
 // words 32l .. 32l+31) free of shared-memory bank conflicts
 #define TW_CIDX(w) ((w) + ((w) >> 5))
-struct TileWarpSmem {
-	uint32_t keys[TBK_NPIX_TILE];         // bucketed float bit patterns
-	uint32_t cnt[TW_WORDS + TW_WORDS / 32]; // packed uint16 pairs: counts -> starts -> ends
+#define TW_CNT_WORDS (TW_WORDS + TW_WORDS / 32)
+
+template <typename K>
+struct TwSmem {
+	K keys[TBK_NPIX_TILE];          // bucketed keys
+	uint32_t cnt[TW_CNT_WORDS];     // packed uint16 pairs: counts -> starts -> ends
 };
+typedef TwSmem<uint32_t> TileWarpSmem;
 
 struct TwBinMap {
 	float scale, off;
 };
+struct TwBinMap64 {
+	double scale, off, lo_c, hi_c;
+};
 
-// Monotone non-decreasing map value -> bin: one FFMA onto the 2^23 "magic" range, then an integer clamp.
-// off >= 2^22 and x >= 0, scale > 0 guarantee t > 0, so the float bit pattern is monotone in t.
-__device__ __forceinline__ int tw_bin(const TwBinMap& m, float x)
-{
-	const float t = fmaf(x, m.scale, m.off);
-	const int b = __float_as_int(t) - 0x4B000000;
-	return max(0, min(TW_NB - 1, b));
-}
+// ---- key traits: float32 pixels (non-negative) and float64 residuals (any sign) ---------------
+struct TwF32 {
+	typedef uint32_t K;
+	typedef TwBinMap Map;
+	static constexpr int NBITS = 32;
+	__device__ static __forceinline__ K invalid() { return TW_INVALID; }
+	__device__ static __forceinline__ K minkey() { return 0u; }
+	__device__ static __forceinline__ K maxkey() { return 0x7f7fffffu; }
+	__device__ static __forceinline__ K padkey() { return 0xFFFFFFFFu; }
+	__device__ static __forceinline__ double val(K k) { return (double)__uint_as_float(k); }
+	// Monotone non-decreasing map value -> bin: one FFMA onto the 2^23 "magic" range, then an integer clamp.
+	// off >= 2^22 and x >= 0, scale > 0 guarantee t > 0, so the float bit pattern is monotone in t.
+	__device__ static __forceinline__ int bin(const Map& m, K k)
+	{
+		const float t = fmaf(__uint_as_float(k), m.scale, m.off);
+		const int b = __float_as_int(t) - 0x4B000000;
+		return max(0, min(TW_NB - 1, b));
+	}
+	// smallest float32 >= d / largest float32 <= d as keys (exact translation of a float64 bound)
+	__device__ static __forceinline__ K key_ceil(double d)
+	{
+		if (!(d > 0.0)) return 0u;
+		float f = (float)d;
+		if ((double)f < d) f = __uint_as_float(__float_as_uint(f) + 1u);
+		return min(__float_as_uint(f), 0x7f7fffffu + 1u);
+	}
+	__device__ static __forceinline__ bool key_floor(double d, K& key)
+	{
+		if (d < 0.0) return false;                // nothing is <= a negative bound
+		if (d == 0.0) { key = 0u; return true; }  // +-0: only zeros qualify
+		float f = (float)d;
+		if ((double)f > d) f = __uint_as_float(__float_as_uint(f) - 1u);
+		key = min(__float_as_uint(f), 0x7f7fffffu);
+		return true;
+	}
+};
 
-__device__ __forceinline__ uint32_t tw_cend(const TileWarpSmem& sm, int b)
+struct TwF64 {
+	typedef unsigned long long K;
+	typedef TwBinMap64 Map;
+	static constexpr int NBITS = 64;
+	__device__ static __forceinline__ K invalid() { return ~0ULL; }
+	__device__ static __forceinline__ K minkey() { return 0ULL; }
+	__device__ static __forceinline__ K maxkey() { return 0xFFEFFFFFFFFFFFFFULL; }  // dkey(DBL_MAX)
+	__device__ static __forceinline__ K padkey() { return ~0ULL; }
+	__device__ static __forceinline__ double val(K k) { return dkey_inv(k); }
+	__device__ static __forceinline__ int bin(const Map& m, K k)
+	{
+		const double dc = fmin(fmax(dkey_inv(k), m.lo_c), m.hi_c);
+		const double t = fma(dc, m.scale, m.off);   // in [2^52 - 1, 2^52 + NB + 1]: integer spacing
+		const long long b = __double_as_longlong(t) - 0x4330000000000000LL;
+		return (int)max(0LL, min((long long)(TW_NB - 1), b));
+	}
+	__device__ static __forceinline__ K key_ceil(double d) { return dkey(d); }
+	__device__ static __forceinline__ bool key_floor(double d, K& key) { key = dkey(d); return true; }
+};
+
+__device__ __forceinline__ uint32_t tw_cend(const uint32_t* cnt, int b)
 {
-	return (sm.cnt[TW_CIDX(b >> 1)] >> ((b & 1) << 4)) & 0xFFFFu;
+	return (cnt[TW_CIDX(b >> 1)] >> ((b & 1) << 4)) & 0xFFFFu;
 }
-__device__ __forceinline__ uint32_t tw_cstart(const TileWarpSmem& sm, int b)
+__device__ __forceinline__ uint32_t tw_cstart(const uint32_t* cnt, int b)
 {
-	return b ? tw_cend(sm, b - 1) : 0u;
+	return b ? tw_cend(cnt, b - 1) : 0u;
 }
 
 // smallest bin b with cend(b) > P  (P < total)
-__device__ __forceinline__ int tw_find_bin(const TileWarpSmem& sm, uint32_t P, int lane)
+__device__ __forceinline__ int tw_find_bin(const uint32_t* cnt, uint32_t P, int lane)
 {
-	unsigned m = __ballot_sync(0xffffffffu, tw_cend(sm, 64 * lane + 63) > P);
+	unsigned m = __ballot_sync(0xffffffffu, tw_cend(cnt, 64 * lane + 63) > P);
 	const int g = __ffs(m) - 1;
-	m = __ballot_sync(0xffffffffu, tw_cend(sm, 64 * g + 2 * lane + 1) > P);
+	m = __ballot_sync(0xffffffffu, tw_cend(cnt, 64 * g + 2 * lane + 1) > P);
 	const int h = __ffs(m) - 1;
 	const int b = 64 * g + 2 * h;
-	return (tw_cend(sm, b) > P) ? b : b + 1;
+	return (tw_cend(cnt, b) > P) ? b : b + 1;
 }
 
-__device__ __forceinline__ uint32_t warp_bitonic32(uint32_t v, int lane)
+template <typename K>
+__device__ __forceinline__ K warp_bitonic32(K v, int lane)
 {
 #pragma unroll
 	for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
 		for (int j = k >> 1; j > 0; j >>= 1) {
-			const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+			const K o = __shfl_xor_sync(0xffffffffu, v, j);
 			const bool up = (lane & k) == 0, lower = (lane & j) == 0;
 			v = (lower == up) ? min(v, o) : max(v, o);
 		}
@@ -77,67 +133,51 @@ __device__ __forceinline__ uint32_t warp_bitonic32(uint32_t v, int lane)
 }
 
 // keys at sorted ranks q and q+1 (when want2) among the span [s, e) of one bin (unsorted inside).
-__device__ __noinline__ void tw_select_in_span(const TileWarpSmem& sm, uint32_t s, uint32_t e, uint32_t q, bool want2,
-	int lane, uint32_t& k1, uint32_t& k2)
+template <typename T>
+__device__ __noinline__ void tw_select_in_span(const typename T::K* keys, uint32_t s, uint32_t e, uint32_t q, bool want2,
+	int lane, typename T::K& k1, typename T::K& k2)
 {
+	typedef typename T::K K;
 	const uint32_t m = e - s;
 	if (m <= 32u) {
-		uint32_t v = (s + lane < e) ? sm.keys[s + lane] : 0xFFFFFFFFu;
-		v = warp_bitonic32(v, lane);
+		K v = (s + lane < e) ? keys[s + lane] : T::padkey();
+		v = warp_bitonic32<K>(v, lane);
 		k1 = __shfl_sync(0xffffffffu, v, q);
 		k2 = want2 ? __shfl_sync(0xffffffffu, v, min(q + 1u, 31u)) : k1;
 		return;
 	}
 	// large bin: exact radix selection on the key bits (MSB first), one sweep of the span per bit
 	for (int r = 0; r < (want2 ? 2 : 1); ++r) {
-		uint32_t target = q + r, prefix = 0;
-		for (int bit = 31; bit >= 0; --bit) {
-			const uint32_t mask = ~((1u << bit) - 1u);      // bits above and including ``bit``
+		uint32_t target = q + r;
+		K prefix = 0;
+		for (int bit = T::NBITS - 1; bit >= 0; --bit) {
+			const K mask = ~((((K)1) << bit) - (K)1);     // bits above and including ``bit``
 			int c0 = 0;
-			for (uint32_t p = s + lane; p < e; p += 32) {
-				const uint32_t k = sm.keys[p];
-				c0 += ((k & mask) == prefix) ? 1 : 0;          // same upper bits, this bit = 0
-			}
+			for (uint32_t p = s + lane; p < e; p += 32) c0 += ((keys[p] & mask) == prefix) ? 1 : 0;
 			c0 = __reduce_add_sync(0xffffffffu, c0);
-			if (target >= (uint32_t)c0) { target -= c0; prefix |= (1u << bit); }
+			if (target >= (uint32_t)c0) { target -= c0; prefix |= (((K)1) << bit); }
 		}
 		if (r == 0) k1 = prefix; else k2 = prefix;
 	}
 	if (!want2) k2 = k1;
 }
 
-// median (mean of the keys at sorted ranks P and P+1 when ``even``) by bin lookup
-__device__ __forceinline__ double tw_median_at(const TileWarpSmem& sm, uint32_t P, bool even, int lane)
+// median (mean of the values at sorted ranks P and P+1 when ``even``) by bin lookup
+template <typename T>
+__device__ __forceinline__ double tw_median_at(const typename T::K* keys, const uint32_t* cnt, uint32_t P, bool even, int lane)
 {
-	const int b = tw_find_bin(sm, P, lane);
-	const uint32_t bs = tw_cstart(sm, b), be = tw_cend(sm, b);
-	uint32_t k1, k2;
+	typedef typename T::K K;
+	const int b = tw_find_bin(cnt, P, lane);
+	const uint32_t bs = tw_cstart(cnt, b), be = tw_cend(cnt, b);
+	K k1, k2;
 	const bool second_here = even && (P + 1u < be);
-	tw_select_in_span(sm, bs, be, P - bs, second_here, lane, k1, k2);
+	tw_select_in_span<T>(keys, bs, be, P - bs, second_here, lane, k1, k2);
 	if (even && !second_here) {
-		const int b2 = tw_find_bin(sm, P + 1u, lane);
-		uint32_t dummy;
-		tw_select_in_span(sm, tw_cstart(sm, b2), tw_cend(sm, b2), 0u, false, lane, k2, dummy);
+		const int b2 = tw_find_bin(cnt, P + 1u, lane);
+		K dummy;
+		tw_select_in_span<T>(keys, tw_cstart(cnt, b2), tw_cend(cnt, b2), 0u, false, lane, k2, dummy);
 	}
-	return 0.5 * ((double)__uint_as_float(k1) + (double)__uint_as_float(k2));
-}
-
-// smallest float32 >= d and largest float32 <= d, as keys clamped to the non-negative finite range
-__device__ __forceinline__ uint32_t tw_key_ceil(double d)
-{
-	if (!(d > 0.0)) return 0u;
-	float f = (float)d;                       // round to nearest
-	if ((double)f < d) f = __uint_as_float(__float_as_uint(f) + 1u);
-	return min(__float_as_uint(f), 0x7f7fffffu + 1u);  // may become +inf key: nothing is >= it
-}
-__device__ __forceinline__ bool tw_key_floor(double d, uint32_t& key)
-{
-	if (d < 0.0) return false;                // nothing is <= a negative bound
-	if (d == 0.0) { key = 0u; return true; }  // +-0: only zeros qualify
-	float f = (float)d;
-	if ((double)f > d) f = __uint_as_float(__float_as_uint(f) - 1u);  // f > d >= 0 so f > 0
-	key = min(__float_as_uint(f), 0x7f7fffffu);
-	return true;
+	return 0.5 * (T::val(k1) + T::val(k2));
 }
 
 __device__ __forceinline__ double warp_sum_d(double v)
@@ -147,8 +187,127 @@ __device__ __forceinline__ double warp_sum_d(double v)
 	return v;
 }
 
-// The per-warp statistics.  ``v`` holds the lane's 128 pixels as float bit patterns (TW_INVALID = masked),
-// nvalid / kmin are warp-uniform.  Returns the result in every lane.
+// Exclusive scan of the packed counters by one warp (32 words = 64 bins per lane): counts -> bin starts.
+__device__ __forceinline__ void tw_scan_counts(uint32_t* cnt, int lane)
+{
+	uint32_t tot = 0;
+#pragma unroll 8
+	for (int j = 0; j < 32; ++j) { const uint32_t w = cnt[lane * 33 + j]; tot += (w & 0xFFFFu) + (w >> 16); }
+	uint32_t inc = tot;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	uint32_t run = inc - tot;
+#pragma unroll 8
+	for (int j = 0; j < 32; ++j) {
+		const uint32_t w = cnt[lane * 33 + j];
+		const uint32_t c0 = w & 0xFFFFu, c1 = w >> 16;
+		cnt[lane * 33 + j] = run | ((run + c0) << 16);
+		run += c0 + c1;
+	}
+}
+
+// The clip iterations + final statistics on bucketed keys (one warp).  Inputs: the moments about
+// ``pivot`` of the core bins [t0e, t1s) (s1c, s2c) and of the two overflow bins (tn, t1, t2).
+template <typename T>
+__device__ TileStat tw_iterate(const typename T::K* keys, const uint32_t* cnt, const typename T::Map& bm,
+	int nvalid, double pivot, double s1c, double s2c, int tn, double t1, double t2, int lane)
+{
+	typedef typename T::K K;
+	TileStat out;
+	out.mean = out.med = out.std = nan_d();
+	out.nfin = 0; out.pad = 0;
+	const uint32_t t0e = tw_cend(cnt, 0);                // [0, t0e)       = low overflow bin
+	const uint32_t t1s = tw_cstart(cnt, TW_NB - 1);      // [t1s, nvalid)  = high overflow bin
+	const uint32_t ntail = t0e + ((uint32_t)nvalid - t1s);
+	int nc = (int)(t1s - t0e);
+
+	K lo_key = T::minkey(), hi_key = T::maxkey();        // running intersection (inclusive)
+	K lo_last = T::minkey(), hi_last = T::maxkey();      // last bounds (inclusive)
+	bool hi_last_ok = true, nested_last = true, converged = false, exhausted = false, empty_run = false;
+	uint32_t below = 0u;                                 // valid elements with key < lo_key
+	int n_prev = -1, n = 0;
+	double med = 0.0, mean = 0.0, sd = 0.0;
+
+	for (int it = 0; it < 6; ++it) {
+		const int ncur = nc + tn;
+		if (it > 0 && ncur == n_prev) { converged = true; break; }   // stats of the previous pass stand
+		n = ncur;
+		if (n == 0) { empty_run = true; break; }
+		const double m1 = (s1c + t1) / (double)n;
+		mean = pivot + m1;
+		sd = sqrt(fmax((s2c + t2) / (double)n - m1 * m1, 0.0));
+		med = tw_median_at<T>(keys, cnt, below + (uint32_t)((n - 1) >> 1), (n & 1) == 0, lane);
+		if (it == 5) { exhausted = true; break; }   // five bound computations done: buffer after the last clip
+		lo_last = T::key_ceil(med - 3.0 * sd);
+		hi_last_ok = T::key_floor(med + 3.0 * sd, hi_last);
+		nested_last = (lo_last >= lo_key) && hi_last_ok && (hi_last <= hi_key);
+		const K new_lo = max(lo_key, lo_last);
+		const K new_hi = hi_last_ok ? min(hi_key, hi_last) : T::minkey();
+		n_prev = n;
+		if (!hi_last_ok || new_lo > new_hi) { empty_run = true; break; }  // cannot happen for finite data
+		if (new_lo == lo_key && new_hi == hi_key) continue;               // nothing can leave: next pass converges
+		// one sweep: (a) core-bin elements leaving the buffer, (b) everything removed below (for ``below``),
+		// (c) the overflow-bin elements still inside the new bounds
+		uint32_t sL = 0, eL = 0, sH = 0, eH = 0;
+		if (new_lo > lo_key) { sL = tw_cstart(cnt, T::bin(bm, lo_key)); eL = tw_cend(cnt, T::bin(bm, new_lo)); }
+		if (new_hi < hi_key) { sH = tw_cstart(cnt, T::bin(bm, new_hi)); eH = tw_cend(cnt, T::bin(bm, hi_key)); }
+		const uint32_t nL = eL - sL, nH = eH - sH;
+		int rn = 0, rc = 0; double r1 = 0.0, r2 = 0.0;
+		for (uint32_t j = lane; j < nL + nH; j += 32) {
+			const uint32_t p = j < nL ? sL + j : sH + (j - nL);
+			const K k = keys[p];
+			const bool gone_lo = (j < nL) && k >= lo_key && k < new_lo;
+			const bool gone_hi = (j >= nL) && k > new_hi && k <= hi_key;
+			if (gone_lo) ++rn;
+			if ((gone_lo || gone_hi) && p >= t0e && p < t1s) {
+				const double d = T::val(k) - pivot; ++rc; r1 += d; r2 = fma(d, d, r2);
+			}
+		}
+		tn = 0; t1 = 0.0; t2 = 0.0;
+		for (uint32_t j = lane; j < ntail; j += 32) {
+			const uint32_t p = j < t0e ? j : t1s + (j - t0e);
+			const K k = keys[p];
+			if (k >= new_lo && k <= new_hi) { const double d = T::val(k) - pivot; ++tn; t1 += d; t2 = fma(d, d, t2); }
+		}
+		rn = __reduce_add_sync(0xffffffffu, rn); rc = __reduce_add_sync(0xffffffffu, rc);
+		if (rc) { r1 = warp_sum_d(r1); r2 = warp_sum_d(r2); nc -= rc; s1c -= r1; s2c -= r2; }
+		if (ntail) { tn = __reduce_add_sync(0xffffffffu, tn); t1 = warp_sum_d(t1); t2 = warp_sum_d(t2); }
+		below += (uint32_t)rn;
+		lo_key = new_lo; hi_key = new_hi;
+	}
+
+	// ---- final statistics: ORIGINAL valid values inside the last bounds
+	if (empty_run || !hi_last_ok || lo_last > hi_last) return out;
+	if ((converged || exhausted) && nested_last) {
+		// last bounds lie inside the previous buffer range, so the final set IS the current buffer, whose
+		// count / mean / median / std(ddof=0 about the mean) were just computed
+		out.nfin = n; out.mean = mean; out.med = med; out.std = sd;
+		return out;
+	}
+	// general case (bounds not nested): direct evaluation over the bin range of the last bounds
+	{
+		const int b0 = T::bin(bm, lo_last), b1 = T::bin(bm, hi_last);
+		const uint32_t s = tw_cstart(cnt, b0), e = tw_cend(cnt, b1);
+		int fn = 0, nb = 0; double f1 = 0.0, f2 = 0.0;
+		for (uint32_t p = s + lane; p < e; p += 32) {
+			const K k = keys[p];
+			if (k < lo_last) ++nb;
+			else if (k <= hi_last) { const double d = T::val(k) - pivot; ++fn; f1 += d; f2 = fma(d, d, f2); }
+		}
+		fn = __reduce_add_sync(0xffffffffu, fn); nb = __reduce_add_sync(0xffffffffu, nb);
+		f1 = warp_sum_d(f1); f2 = warp_sum_d(f2);
+		out.nfin = fn;
+		if (fn == 0) return out;
+		const double m1 = f1 / (double)fn;
+		out.mean = pivot + m1;
+		out.std = sqrt(fmax(f2 / (double)fn - m1 * m1, 0.0));
+		out.med = tw_median_at<T>(keys, cnt, s + (uint32_t)nb + (uint32_t)((fn - 1) >> 1), (fn & 1) == 0, lane);
+	}
+	return out;
+}
+
+// The per-warp statistics for float32 pixels.  ``v`` holds the lane's 128 pixels as float bit patterns
+// (TW_INVALID = masked), nvalid / kmin are warp-uniform.  Returns the result in every lane.
 __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32_t kmin,
 	TileWarpSmem& sm, int lane)
 {
@@ -167,7 +326,7 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 		float med = 0.f, iqr = 0.f; int sets = 0;
 #pragma unroll
 		for (int t = 0; t < 2; ++t) {
-			const uint32_t k = warp_bitonic32(t ? sb : sa, lane);
+			const uint32_t k = warp_bitonic32<uint32_t>(t ? sb : sa, lane);
 			const int m = __popc(__ballot_sync(0xffffffffu, k != TW_INVALID));
 			if (m >= 8) {
 				med += __uint_as_float(__shfl_sync(0xffffffffu, k, m >> 1));
@@ -201,32 +360,16 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 	const double pivot = (double)pivot_f;
 
 	// ---- pass 1: bin counts
-	for (int i = lane; i < TW_WORDS + TW_WORDS / 32; i += 32) sm.cnt[i] = 0u;
+	for (int i = lane; i < TW_CNT_WORDS; i += 32) sm.cnt[i] = 0u;
 	__syncwarp();
 #pragma unroll
 	for (int e = 0; e < 128; ++e) {
 		const uint32_t k = v[e];
-		const int b = tw_bin(bm, __uint_as_float(k));
+		const int b = TwF32::bin(bm, k);
 		if (k != TW_INVALID) atomicAdd(&sm.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4));
 	}
 	__syncwarp();
-	// ---- exclusive scan of the packed counters (32 words = 64 bins per lane)
-	{
-		uint32_t tot = 0;
-#pragma unroll 8
-		for (int j = 0; j < 32; ++j) { const uint32_t w = sm.cnt[lane * 33 + j]; tot += (w & 0xFFFFu) + (w >> 16); }
-		uint32_t inc = tot;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-		uint32_t run = inc - tot;
-#pragma unroll 8
-		for (int j = 0; j < 32; ++j) {
-			const uint32_t w = sm.cnt[lane * 33 + j];
-			const uint32_t c0 = w & 0xFFFFu, c1 = w >> 16;
-			sm.cnt[lane * 33 + j] = run | ((run + c0) << 16);
-			run += c0 + c1;
-		}
-	}
+	tw_scan_counts(sm.cnt, lane);
 	__syncwarp();
 	// ---- pass 2: scatter in groups of 8 (the counters advance from bin starts to bin ends)
 #pragma unroll
@@ -235,7 +378,7 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 #pragma unroll
 		for (int j = 0; j < 8; ++j) {
 			const uint32_t k = v[8 * g + j];
-			const int b = tw_bin(bm, __uint_as_float(k));
+			const int b = TwF32::bin(bm, k);
 			sh[j] = (b & 1) << 4;
 			old[j] = 0u;
 			if (k != TW_INVALID) old[j] = atomicAdd(&sm.cnt[TW_CIDX(b >> 1)], 1u << sh[j]);
@@ -249,8 +392,8 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 	__syncwarp();
 
 	// ---- moments about the pivot: core bins [t0e, t1s) and the two overflow bins
-	const uint32_t t0e = tw_cend(sm, 0);                // [0, t0e)       = low overflow bin
-	const uint32_t t1s = tw_cstart(sm, TW_NB - 1);      // [t1s, nvalid)  = high overflow bin
+	const uint32_t t0e = tw_cend(sm.cnt, 0);
+	const uint32_t t1s = tw_cstart(sm.cnt, TW_NB - 1);
 	const uint32_t ntail = t0e + ((uint32_t)nvalid - t1s);
 	double s1c = 0.0, s2c = 0.0;
 	{
@@ -264,15 +407,6 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 		if (p < t1s) { const double d0 = (double)__uint_as_float(sm.keys[p]) - pivot; a1 += d0; a2 = fma(d0, d0, a2); }
 		s1c = warp_sum_d(a1 + b1); s2c = warp_sum_d(a2 + b2);
 	}
-	int nc = (int)(t1s - t0e);
-
-	uint32_t lo_key = 0u, hi_key = 0x7f7fffffu;         // running intersection (inclusive)
-	uint32_t lo_last = 0u, hi_last = 0x7f7fffffu;       // last bounds (inclusive)
-	bool hi_last_ok = true, nested_last = true, converged = false, exhausted = false, empty_run = false;
-	uint32_t below = 0u;                                // valid elements with key < lo_key
-	int n_prev = -1, n = 0;
-	double med = 0.0, mean = 0.0, sd = 0.0;
-	// in-range part of the overflow bins (direct sums, recomputed whenever the bounds move)
 	int tn = 0; double t1 = 0.0, t2 = 0.0;
 	for (uint32_t j = lane; j < ntail; j += 32) {
 		const uint32_t p = j < t0e ? j : t1s + (j - t0e);
@@ -280,81 +414,122 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 		++tn; t1 += d; t2 = fma(d, d, t2);
 	}
 	if (ntail) { tn = __reduce_add_sync(0xffffffffu, tn); t1 = warp_sum_d(t1); t2 = warp_sum_d(t2); }
+	return tw_iterate<TwF32>(sm.keys, sm.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
+}
 
-	for (int it = 0; it < 6; ++it) {
-		const int ncur = nc + tn;
-		if (it > 0 && ncur == n_prev) { converged = true; break; }   // stats of the previous pass stand
-		n = ncur;
-		if (n == 0) { empty_run = true; break; }
-		const double m1 = (s1c + t1) / (double)n;
-		mean = pivot + m1;
-		sd = sqrt(fmax((s2c + t2) / (double)n - m1 * m1, 0.0));
-		med = tw_median_at(sm, below + (uint32_t)((n - 1) >> 1), (n & 1) == 0, lane);
-		if (it == 5) { exhausted = true; break; }   // five bound computations done: buffer after the last clip
-		lo_last = tw_key_ceil(med - 3.0 * sd);
-		hi_last_ok = tw_key_floor(med + 3.0 * sd, hi_last);
-		nested_last = (lo_last >= lo_key) && hi_last_ok && (hi_last <= hi_key);
-		const uint32_t new_lo = max(lo_key, lo_last);
-		const uint32_t new_hi = hi_last_ok ? min(hi_key, hi_last) : 0u;
-		n_prev = n;
-		if (!hi_last_ok || new_lo > new_hi) { empty_run = true; break; }  // cannot happen for finite data
-		if (new_lo == lo_key && new_hi == hi_key) continue;               // nothing can leave: next pass converges
-		// one sweep: (a) core-bin elements leaving the buffer, (b) everything removed below (for ``below``),
-		// (c) the overflow-bin elements still inside the new bounds
-		uint32_t sL = 0, eL = 0, sH = 0, eH = 0;
-		if (new_lo > lo_key) { sL = tw_cstart(sm, tw_bin(bm, __uint_as_float(lo_key))); eL = tw_cend(sm, tw_bin(bm, __uint_as_float(new_lo))); }
-		if (new_hi < hi_key) { sH = tw_cstart(sm, tw_bin(bm, __uint_as_float(new_hi))); eH = tw_cend(sm, tw_bin(bm, __uint_as_float(hi_key))); }
-		const uint32_t nL = eL - sL, nH = eH - sH;
-		int rn = 0, rc = 0; double r1 = 0.0, r2 = 0.0;
-		for (uint32_t j = lane; j < nL + nH; j += 32) {
-			const uint32_t p = j < nL ? sL + j : sH + (j - nL);
-			const uint32_t k = sm.keys[p];
-			const bool gone_lo = (j < nL) && k >= lo_key && k < new_lo;
-			const bool gone_hi = (j >= nL) && k > new_hi && k <= hi_key;
-			if (gone_lo) ++rn;
-			if ((gone_lo || gone_hi) && p >= t0e && p < t1s) {
-				const double d = (double)__uint_as_float(k) - pivot; ++rc; r1 += d; r2 = fma(d, d, r2);
+// ---------------------------------------------------------------------------------------------
+// Float64 residuals (x - radial): one CTA of 128 threads per mesh, 32 values per thread.  The four warps
+// share the counters / key buffer for the two passes; warp 0 alone runs the iterations.
+struct TileRound64Smem {
+	TwSmem<unsigned long long> tw;
+	TwBinMap64 bm;
+	double pivot;
+	double red[2][4][3];
+	unsigned long long kmin, kmax;
+	int nvalid, ntl[4], constant;
+};
+
+__device__ void tile_block_stats64(const unsigned long long (&key)[32], TileRound64Smem& sm, TileStat& out, bool& writer)
+{
+	typedef unsigned long long K;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	writer = (tid == 0);
+	out.mean = out.med = out.std = nan_d();
+	out.nfin = 0; out.pad = 0;
+	// ---- count, min, max
+	int n = 0; K kmin = ~0ULL, kmax = 0ULL;
+#pragma unroll
+	for (int e = 0; e < 32; ++e) {
+		const K k = key[e];
+		if (k != ~0ULL) { ++n; kmin = min(kmin, k); kmax = max(kmax, k); }
+	}
+	n = __reduce_add_sync(0xffffffffu, n);
+	for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
+	if (tid == 0) { sm.nvalid = 0; sm.kmin = ~0ULL; sm.kmax = 0ULL; sm.constant = 0; }
+	for (int i = tid; i < TW_CNT_WORDS; i += 128) sm.tw.cnt[i] = 0u;
+	__syncthreads();
+	if (lane == 0) { atomicAdd(&sm.nvalid, n); atomicMin(&sm.kmin, kmin); atomicMax(&sm.kmax, kmax); }
+	__syncthreads();
+	const int nvalid = sm.nvalid;
+	if (nvalid == 0) return;
+	// ---- robust window from warp 0's samples (its rows are spread over the whole mesh)
+	if (w == 0) {
+		const int sel = lane & 3;
+		const K sa = sel == 0 ? key[0] : sel == 1 ? key[9] : sel == 2 ? key[18] : key[27];
+		const K sb = sel == 0 ? key[14] : sel == 1 ? key[23] : sel == 2 ? key[4] : key[29];
+		double med = 0.0, iqr = 0.0; int sets = 0;
+#pragma unroll
+		for (int t = 0; t < 2; ++t) {
+			const K k = warp_bitonic32<K>(t ? sb : sa, lane);
+			const int m = __popc(__ballot_sync(0xffffffffu, k != ~0ULL));
+			if (m >= 8) {
+				med += dkey_inv(__shfl_sync(0xffffffffu, k, m >> 1));
+				iqr += dkey_inv(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - dkey_inv(__shfl_sync(0xffffffffu, k, m >> 2));
+				++sets;
 			}
 		}
-		tn = 0; t1 = 0.0; t2 = 0.0;
-		for (uint32_t j = lane; j < ntail; j += 32) {
-			const uint32_t p = j < t0e ? j : t1s + (j - t0e);
-			const uint32_t k = sm.keys[p];
-			if (k >= new_lo && k <= new_hi) { const double d = (double)__uint_as_float(k) - pivot; ++tn; t1 += d; t2 = fma(d, d, t2); }
+		if (lane == 0) {
+			double w0, w1, pv;
+			const double vmin = dkey_inv(sm.kmin), vmax = dkey_inv(sm.kmax);
+			if (sets && iqr > 0.0) {
+				med /= (double)sets;
+				const double half = 10.0 * (iqr / (double)sets) / 1.349;
+				w0 = med - half; w1 = med + half; pv = med;
+			} else {
+				w0 = vmin; w1 = vmax; pv = vmin;
+				if (!(vmax > vmin)) sm.constant = 1;
+			}
+			TwBinMap64 bm;
+			bm.scale = (double)(TW_NB - 2) / (w1 - w0);
+			if (!(bm.scale < 1e300)) bm.scale = 1e300;
+			bm.lo_c = w0 - 1.5 / bm.scale; bm.hi_c = w1 + 1.5 / bm.scale;
+			bm.off = fma(-w0, bm.scale, 4503599627370497.0);  // 2^52 + 1
+			sm.bm = bm; sm.pivot = pv;
 		}
-		rn = __reduce_add_sync(0xffffffffu, rn); rc = __reduce_add_sync(0xffffffffu, rc);
-		if (rc) { r1 = warp_sum_d(r1); r2 = warp_sum_d(r2); nc -= rc; s1c -= r1; s2c -= r2; }
-		if (ntail) { tn = __reduce_add_sync(0xffffffffu, tn); t1 = warp_sum_d(t1); t2 = warp_sum_d(t2); }
-		below += (uint32_t)rn;
-		lo_key = new_lo; hi_key = new_hi;
 	}
-
-	// ---- final statistics: ORIGINAL valid values inside the last bounds
-	if (empty_run || !hi_last_ok || lo_last > hi_last) return out;
-	if ((converged || exhausted) && nested_last) {
-		// last bounds lie inside the previous buffer range, so the final set IS the current buffer, whose
-		// count / mean / median / std(ddof=0 about the mean) were just computed
-		out.nfin = n; out.mean = mean; out.med = med; out.std = sd;
-		return out;
+	__syncthreads();
+	if (sm.constant) {  // all residuals equal: sigma = 0, nothing is clipped
+		out.mean = out.med = dkey_inv(sm.kmin); out.std = 0.0; out.nfin = nvalid;
+		return;
 	}
-	// general case (bounds not nested): direct evaluation over the bin range of the last bounds
-	{
-		const int b0 = tw_bin(bm, __uint_as_float(lo_last)), b1 = tw_bin(bm, __uint_as_float(hi_last));
-		const uint32_t s = tw_cstart(sm, b0), e = tw_cend(sm, b1);
-		int fn = 0, nb = 0; double f1 = 0.0, f2 = 0.0;
-		for (uint32_t p = s + lane; p < e; p += 32) {
-			const uint32_t k = sm.keys[p];
-			if (k < lo_last) ++nb;
-			else if (k <= hi_last) { const double d = (double)__uint_as_float(k) - pivot; ++fn; f1 += d; f2 = fma(d, d, f2); }
+	const TwBinMap64 bm = sm.bm;
+	const double pivot = sm.pivot;
+	// ---- pass 1: counts
+#pragma unroll
+	for (int e = 0; e < 32; ++e) {
+		const K k = key[e];
+		if (k != ~0ULL) { const int b = TwF64::bin(bm, k); atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4)); }
+	}
+	__syncthreads();
+	if (w == 0) tw_scan_counts(sm.tw.cnt, lane);
+	__syncthreads();
+	// ---- pass 2: scatter
+#pragma unroll
+	for (int e = 0; e < 32; ++e) {
+		const K k = key[e];
+		if (k != ~0ULL) {
+			const int b = TwF64::bin(bm, k);
+			const int sh = (b & 1) << 4;
+			const uint32_t old = atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << sh);
+			sm.tw.keys[(old >> sh) & 0xFFFFu] = k;
 		}
-		fn = __reduce_add_sync(0xffffffffu, fn); nb = __reduce_add_sync(0xffffffffu, nb);
-		f1 = warp_sum_d(f1); f2 = warp_sum_d(f2);
-		out.nfin = fn;
-		if (fn == 0) return out;
-		const double m1 = f1 / (double)fn;
-		out.mean = pivot + m1;
-		out.std = sqrt(fmax(f2 / (double)fn - m1 * m1, 0.0));
-		out.med = tw_median_at(sm, s + (uint32_t)nb + (uint32_t)((fn - 1) >> 1), (fn & 1) == 0, lane);
 	}
-	return out;
+	__syncthreads();
+	// ---- moments: all four warps sweep the bucketed keys
+	const uint32_t t0e = tw_cend(sm.tw.cnt, 0), t1s = tw_cstart(sm.tw.cnt, TW_NB - 1);
+	double c1 = 0.0, c2 = 0.0, q1 = 0.0, q2 = 0.0; int tn = 0;
+	for (uint32_t p = tid; p < (uint32_t)nvalid; p += 128) {
+		const double d = dkey_inv(sm.tw.keys[p]) - pivot;
+		if (p >= t0e && p < t1s) { c1 += d; c2 = fma(d, d, c2); }
+		else { ++tn; q1 += d; q2 = fma(d, d, q2); }
+	}
+	c1 = warp_sum_d(c1); c2 = warp_sum_d(c2); q1 = warp_sum_d(q1); q2 = warp_sum_d(q2);
+	tn = __reduce_add_sync(0xffffffffu, tn);
+	if (lane == 0) { sm.red[0][w][0] = c1; sm.red[0][w][1] = c2; sm.red[1][w][0] = q1; sm.red[1][w][1] = q2; sm.ntl[w] = tn; }
+	__syncthreads();
+	if (w != 0) { writer = false; return; }
+	double s1c = 0.0, s2c = 0.0, t1 = 0.0, t2 = 0.0; tn = 0;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) { s1c += sm.red[0][q][0]; s2c += sm.red[0][q][1]; t1 += sm.red[1][q][0]; t2 += sm.red[1][q][1]; tn += sm.ntl[q]; }
+	out = tw_iterate<TwF64>(sm.tw.keys, sm.tw.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
 }
