@@ -377,12 +377,16 @@ __global__ void k_ring_gather(PlanDev P, Workspace ws, const float* __restrict__
 // K_ring_kde: mode of a Gaussian FFT-KDE per ring (backgrounds.py:21-33 + statsmodels 0.13.2
 // KDEUnivariate.fit(gridsize=2000); see oracle/backgrounds_oracle.py:kde_density).
 #define TBK_KDE_NT 512
+#define TBK_KDE_CAND 256
 struct KdeSmem {
 	double2 x[TBK_KDE_M];
 	SelectSmem sel;
 	RedSmem red;
 	double bestv[32];
 	int besti[32];
+	double qcand[4][TBK_KDE_CAND];   // members of the bins that hold the quartile ranks
+	double qres[4];
+	int qbin[4], qexcl[4], qcnt[4], qn[4];
 };
 
 __device__ __forceinline__ void kde_fft(double2* x, const double2* __restrict__ tw, bool inverse)
@@ -436,17 +440,91 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 	block_sum3(sm.red, nd, ss, dmy);
 	const double sd = sqrt(ss / (double)(n - 1));
 
-	// scipy.stats.scoreatpercentile(x, 25 / 75): linear interpolation at (n-1)*p
+	// scipy.stats.scoreatpercentile(x, 25 / 75): linear interpolation at (n-1)*p.  The (up to) four order
+	// statistics are resolved together: one histogram over mean +- 1.8 std (which always brackets the
+	// quartiles), one collecting sweep; a rank whose bin is an overflow bin or too full falls back to the
+	// generic iterated selection.
 	double q[2];
-	for (int t = 0; t < 2; ++t) {
-		const double idx = (t == 0 ? 0.25 : 0.75) * (double)(n - 1);
-		const int i0 = (int)idx;
-		const double a0 = block_select(sm.sel, sm.red, each, i0, mn, mx);
-		if ((double)i0 == idx) q[t] = a0;
-		else {
-			const double a1 = block_select(sm.sel, sm.red, each, i0 + 1, mn, mx);
-			const double w0 = (double)(i0 + 1) - idx, w1 = idx - (double)i0;
-			q[t] = __dadd_rn(__dmul_rn(a0, w0), __dmul_rn(a1, w1)) / (w0 + w1);
+	{
+		int rk[4]; double fr[2];
+		for (int t = 0; t < 2; ++t) {
+			const double idx = (t == 0 ? 0.25 : 0.75) * (double)(n - 1);
+			const int i0 = (int)idx;
+			fr[t] = idx - (double)i0;
+			rk[2 * t] = i0; rk[2 * t + 1] = (fr[t] > 0.0) ? i0 + 1 : i0;
+		}
+		const double w0 = fmax(mean - 1.8 * sd, mn), w1 = fmin(mean + 1.8 * sd, mx);
+		const double hscale = (double)(TBK_NBINS - 2) / (w1 - w0);
+		const bool fast = (w1 > w0) && (hscale < 1e300);
+		double ord[4];
+		bool done[4] = {false, false, false, false};
+		if (fast) {
+			for (int i = tid; i < TBK_NBINS; i += nt) sm.sel.hist[i] = 0u;
+			if (tid < 4) sm.qn[tid] = 0;
+			__syncthreads();
+			each([&](double d) {
+				const double t = (d - w0) * hscale;
+				const int bin = d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
+				atomicAdd(&sm.sel.hist[bin], 1u);
+			});
+			__syncthreads();
+			// exclusive scan (thread t owns bins 2t, 2t+1 for 512 threads)
+			const int per = TBK_NBINS / TBK_KDE_NT;
+			unsigned loc[2], tsum = 0;
+			for (int j = 0; j < per; ++j) { loc[j] = sm.sel.hist[tid * per + j]; tsum += loc[j]; }
+			unsigned inc = tsum;
+			for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += u; }
+			if ((tid & 31) == 31) sm.sel.wsum[tid >> 5] = inc;
+			__syncthreads();
+			unsigned base = 0;
+			for (int w = 0; w < (tid >> 5); ++w) base += sm.sel.wsum[w];
+			unsigned excl = base + inc - tsum;
+			for (int j = 0; j < per; ++j) {
+				for (int r = 0; r < 4; ++r)
+					if ((unsigned)rk[r] >= excl && (unsigned)rk[r] < excl + loc[j]) { sm.qbin[r] = tid * per + j; sm.qexcl[r] = (int)excl; sm.qcnt[r] = (int)loc[j]; }
+				excl += loc[j];
+			}
+			__syncthreads();
+			int qb[4], qe[4], qc[4];
+			for (int r = 0; r < 4; ++r) { qb[r] = sm.qbin[r]; qe[r] = sm.qexcl[r]; qc[r] = sm.qcnt[r]; }
+			// collect the members of the target bins (ranks in the same bin share list r of the first of them)
+			int lst[4];
+			for (int r = 0; r < 4; ++r) { lst[r] = r; for (int p = 0; p < r; ++p) if (qb[p] == qb[r]) { lst[r] = lst[p]; break; } }
+			each([&](double d) {
+				const double t = (d - w0) * hscale;
+				const int bin = d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
+				for (int r = 0; r < 4; ++r)
+					if (lst[r] == r && bin == qb[r] && qc[r] <= TBK_KDE_CAND && bin != 0 && bin != TBK_NBINS - 1) {
+						const int p = atomicAdd(&sm.qn[r], 1);
+						sm.qcand[r][p] = d;
+					}
+			});
+			__syncthreads();
+			for (int r = 0; r < 4; ++r) {
+				const int L = lst[r];
+				if (qc[L] > TBK_KDE_CAND || qb[r] == 0 || qb[r] == TBK_NBINS - 1) continue;
+				const int cntL = qc[L], kk = rk[r] - qe[r];
+				for (int j = tid; j < cntL; j += nt) {
+					const double cj = sm.qcand[L][j];
+					int rr = 0;
+					for (int i = 0; i < cntL; ++i) { const double ci = sm.qcand[L][i]; rr += (ci < cj) || (ci == cj && i < j); }
+					if (rr == kk) sm.qres[r] = cj;
+				}
+				done[r] = true;
+			}
+			__syncthreads();
+			for (int r = 0; r < 4; ++r) if (done[r]) ord[r] = sm.qres[r];
+		}
+		for (int r = 0; r < 4; ++r) {
+			if (done[r]) continue;
+			if (r > 0 && rk[r] == rk[r - 1]) { ord[r] = ord[r - 1]; continue; }
+			ord[r] = block_select(sm.sel, sm.red, each, rk[r], mn, mx);
+		}
+		for (int t = 0; t < 2; ++t) {
+			if (fr[t] > 0.0) {
+				const double w0q = (double)(rk[2 * t] + 1) - ((t == 0 ? 0.25 : 0.75) * (double)(n - 1)), w1q = fr[t];
+				q[t] = __dadd_rn(__dmul_rn(ord[2 * t], w0q), __dmul_rn(ord[2 * t + 1], w1q)) / (w0q + w1q);
+			} else q[t] = ord[2 * t];
 		}
 	}
 	const double iqr = (q[1] - q[0]) / 1.349;
@@ -466,19 +544,48 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 	const double delta = (bb - a) / (double)(TBK_KDE_M - 1);
 	const double range = bb - a;
 
-	// linear binning (statsmodels linbin.fast_linbin); real part of x[] is the grid
-	for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i] = make_double2(0.0, 0.0);
+	// linear binning (statsmodels linbin.fast_linbin): g[li] += 1 - rem, g[li+1] += rem.  Shared memory has no
+	// native 64-bit add, so each cell keeps a sample count and the sum of rem as 48-bit fixed point in three
+	// 16-bit chunks (four 32-bit atomics per sample, exact for n < 65536 and independent of the arrival
+	// order); then g[c] = count[c] - S[c] + S[c-1].  Larger rings use float64 CAS adds.
+	uint32_t* lb = reinterpret_cast<uint32_t*>(sm.x);   // [4][TBK_KDE_M] overlay on the FFT buffer
+	const bool fixed = n < 65536;
+	if (fixed) { for (int i = tid; i < 4 * TBK_KDE_M; i += nt) lb[i] = 0u; }
+	else { for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i] = make_double2(0.0, 0.0); }
 	__syncthreads();
 	each([&](double d) {
 		const double lxi = (d - a) / delta;
 		const int li = (int)lxi;
 		const double rem = lxi - (double)li;
 		if (li > 1 && li < TBK_KDE_M - 1) {
-			atomicAdd(&sm.x[li].x, 1.0 - rem);
-			atomicAdd(&sm.x[li + 1].x, rem);
+			if (fixed) {
+				const unsigned long long fp = (unsigned long long)(rem * 281474976710656.0);  // rem * 2^48, rem in [0, 1)
+				atomicAdd(&lb[li], 1u);
+				atomicAdd(&lb[TBK_KDE_M + li], (uint32_t)(fp & 0xFFFFu));
+				atomicAdd(&lb[2 * TBK_KDE_M + li], (uint32_t)((fp >> 16) & 0xFFFFu));
+				atomicAdd(&lb[3 * TBK_KDE_M + li], (uint32_t)(fp >> 32));
+			} else {
+				atomicAdd(&sm.x[li].x, 1.0 - rem);
+				atomicAdd(&sm.x[li + 1].x, rem);
+			}
 		}
 	});
 	__syncthreads();
+	if (fixed) {
+		double g[TBK_KDE_M / TBK_KDE_NT];
+		for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) {
+			const int cidx = tid + j * nt;
+			const double S = (double)lb[TBK_KDE_M + cidx] * 3.552713678800501e-15 + (double)lb[2 * TBK_KDE_M + cidx] * 2.3283064365386963e-10
+				+ (double)lb[3 * TBK_KDE_M + cidx] * 1.52587890625e-05;
+			double Sm = 0.0;
+			if (cidx > 0) Sm = (double)lb[TBK_KDE_M + cidx - 1] * 3.552713678800501e-15 + (double)lb[2 * TBK_KDE_M + cidx - 1] * 2.3283064365386963e-10
+				+ (double)lb[3 * TBK_KDE_M + cidx - 1] * 1.52587890625e-05;
+			g[j] = ((double)lb[cidx] - S) + Sm;
+		}
+		__syncthreads();
+		for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
+		__syncthreads();
+	}
 	// bit-reversal permutation + normalisation binned = g / (delta * nobs)
 	const double norm = 1.0 / (delta * (double)n);
 	for (int i = tid; i < TBK_KDE_M; i += nt) {
