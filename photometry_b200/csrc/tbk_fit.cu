@@ -974,10 +974,58 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 
 // ---------------------------------------------------------------------------------------------
 // K_final: bkg = img_bkg_radial + img_bkg_square (backgrounds.py:209), float32.
-__global__ void __launch_bounds__(TBK_NT) k_final(PlanDev P, Workspace ws,
+// Mesh-uniform specialisations keep the per-pixel work at 8 DFMA + add + convert: the clip to
+// [mesh_min, mesh_max] is skipped when the 5x5 coefficient neighbourhood already lies inside that range
+// (a cubic B-spline value is a convex combination of its coefficients), and the radial term is a constant
+// for every mesh that cannot see beyond the first ring centre.
+struct FinalSmem {
+	double c[5][6];          // coefficient neighbourhood, rows padded for 16-byte vector loads
+	double wT[4][64];        // zoom weights transposed: wT[tap][phase] (conflict-free per-lane loads)
+	double mesh_min, mesh_max, c_flat;
+	int mesh_const, radial_ok, need_clip;
+};
+
+template <bool CLIP, bool NONFLAT>
+__device__ __forceinline__ void final_rows(const FinalSmem& z, const RadialSmem2& rs, const PlanDev& P,
+	float* __restrict__ bkg, size_t img, int ty, int tx, int tid)
+{
+	const int lcol = tile_lcol(tid), ox = lcol >> 5;
+	const int gx = tx * TBK_TILE + lcol;
+	double wx[4][4];
+#pragma unroll
+	for (int b = 0; b < 4; ++b) {
+		const double2 u0 = *reinterpret_cast<const double2*>(&z.wT[b][lcol]);
+		const double2 u1 = *reinterpret_cast<const double2*>(&z.wT[b][lcol + 2]);
+		wx[0][b] = u0.x; wx[1][b] = u0.y; wx[2][b] = u1.x; wx[3][b] = u1.y;
+	}
+	const double lo = z.mesh_min, hi = z.mesh_max, cflat = z.radial_ok ? z.c_flat : 0.0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int lrow = tile_lrow(tid, j), oy = lrow >> 5;
+		const int gy = ty * TBK_TILE + lrow;
+		double r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+		for (int a = 0; a < 4; ++a) {
+			const double wy = z.wT[a][lrow];
+#pragma unroll
+			for (int b = 0; b < 4; ++b) r[b] = fma(wy, z.c[oy + a][ox + b], r[b]);
+		}
+		float o[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			double sq = wx[q][0] * r[0] + wx[q][1] * r[1] + wx[q][2] * r[2] + wx[q][3] * r[3];
+			if (CLIP) sq = fmin(fmax(sq, lo), hi);
+			const double rad = NONFLAT ? radial_value_s(rs, pixel_radius(P, gy, gx + q)) : cflat;
+			o[q] = (float)(rad + sq);
+		}
+		*reinterpret_cast<float4*>(bkg + img + (size_t)gy * P.W + gx) = make_float4(o[0], o[1], o[2], o[3]);
+	}
+}
+
+__global__ void __launch_bounds__(TBK_NT, 4) k_final(PlanDev P, Workspace ws,
 	float* __restrict__ bkg, uint8_t* __restrict__ mask_out)
 {
-	__shared__ ZoomTile z;
+	__shared__ FinalSmem z;
 	__shared__ RadialSmem2 rs;
 	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
 	const FfiCtl& c = ws.ctl[b];
@@ -995,28 +1043,35 @@ __global__ void __launch_bounds__(TBK_NT) k_final(PlanDev P, Workspace ws,
 		}
 		return;
 	}
-	zoom_tile_load(z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
-	zoom_tile_stage(z, c, P.zoom_w);
+	const double* coef = ws.coef + (size_t)b * P.ntiles;
+	if (tid < 25) {
+		const int a = tid / 5, bb = tid % 5;
+		z.c[a][bb] = coef[reflect_fold(ty - 2 + a, P.ny) * P.nx + reflect_fold(tx - 2 + bb, P.nx)];
+	}
+	z.wT[tid & 3][tid >> 2] = __ldg(P.zoom_w + tid);
 	const bool nonflat = P.use_radial && c.radial_ok && P.tile_slot[tile] >= 0;
 	if (nonflat) radial_stage(rs, c, P);
 	__syncthreads();
-	const double cflat = (P.use_radial && z.radial_ok) ? z.c_flat : 0.0;
-	ZoomCols zc;
-	zoom_cols_load(zc, z, lcol);
-#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		const int lrow = tile_lrow(tid, j);
-		const int gy = ty * TBK_TILE + lrow;
-		double sq[4];
-		zoom_cols_eval4(zc, z, lrow, sq);
-		float o[4];
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const double rad = nonflat ? radial_value_s(rs, pixel_radius(P, gy, gx + q)) : cflat;
-			o[q] = (float)(rad + zoom_clip_s(z, sq[q]));
+	if (tid == 0) {
+		double cmin = INFINITY, cmax = -INFINITY;
+		for (int a = 0; a < 5; ++a) for (int bb = 0; bb < 5; ++bb) { cmin = fmin(cmin, z.c[a][bb]); cmax = fmax(cmax, z.c[a][bb]); }
+		z.mesh_min = c.mesh_min; z.mesh_max = c.mesh_max; z.mesh_const = c.mesh_const;
+		z.radial_ok = c.radial_ok; z.c_flat = c.c_flat;
+		// small margin: the interpolated value can leave [cmin, cmax] only by rounding
+		const double eps = 1e-12 * fmax(fabs(cmin), fabs(cmax));
+		z.need_clip = !(cmin - eps >= c.mesh_min && cmax + eps <= c.mesh_max);
+		if (c.mesh_const) {  // ptp(mesh) == 0: the map is the constant (BkgZoomInterpolator short-circuit)
+			for (int a = 0; a < 5; ++a) for (int bb = 0; bb < 6; ++bb) z.c[a][bb] = c.mesh_min;
+			z.need_clip = 1;
 		}
-		const size_t off = img + (size_t)gy * P.W + gx;
-		*reinterpret_cast<float4*>(bkg + off) = make_float4(o[0], o[1], o[2], o[3]);
+	}
+	__syncthreads();
+	if (z.need_clip) {
+		if (nonflat) final_rows<true, true>(z, rs, P, bkg, img, ty, tx, tid);
+		else final_rows<true, false>(z, rs, P, bkg, img, ty, tx, tid);
+	} else {
+		if (nonflat) final_rows<false, true>(z, rs, P, bkg, img, ty, tx, tid);
+		else final_rows<false, false>(z, rs, P, bkg, img, ty, tx, tid);
 	}
 }
 
