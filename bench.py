@@ -233,7 +233,7 @@ def run_b200(args):
 		fit.fit(cube[a:b], meta_d[a * isz:b * isz], bkg_out=bkg[a:b], mask_out=mask[a:b], profile=prof)
 	ncalls = (n + chunk - 1) // chunk
 	dom = max((k for k in prof if k != 'misc'), key=lambda k: prof[k])
-	launches_per_call = {'tile_base': 1, 'tile_round': 3, 'zp_min': 2, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
+	launches_per_call = {'tile_base': 1, 'tile_round': 3, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
 	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
 	peak, peak_src = load_peaks()
 	achieved = ALGO_BYTES_PER_FFI * min(chunk, n) / (dom_launch_ms * 1e-3) / 1e9
@@ -337,7 +337,7 @@ def main():
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--ffis', type=int, default=1340, help='FFIs per GPU per step')
-	ap.add_argument('--chunk', type=int, default=16, help='FFIs per tbk_fit_batch launch')
+	ap.add_argument('--chunk', type=int, default=64, help='FFIs per tbk_fit_batch launch')
 	ap.add_argument('--e2e-ffis', type=int, default=128, help='pinned host sample size for the end-to-end leg')
 	ap.add_argument('--prepare-ffis', type=int, default=256)
 	ap.add_argument('--no-prepare', dest='prepare', action='store_false')

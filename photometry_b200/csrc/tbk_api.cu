@@ -32,7 +32,7 @@ struct tbk_plan {
 	int* zero_flags;
 	int zero_cap;
 	int tile_kernel;   // 0: CTA-per-mesh generic kernel, 1: warp-per-mesh register kernel (default)
-	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin;
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow;
 };
 
 // photometry/backgrounds.py:121-138
@@ -88,6 +88,7 @@ static void layout(tbk_plan* p, int B, size_t* total)
 	p->off_s2hist = o; o = align_up(o + sizeof(double) * (size_t)B * P.bkgiters * std::max(P.nrings, 1));
 	p->off_ringv = o;  o = align_up(o + sizeof(double) * (size_t)B * std::max(P.nringpix, 1));
 	p->off_sbmin = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
+	p->off_sblow = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
 	*total = o;
 }
 
@@ -106,6 +107,7 @@ static Workspace carve(tbk_plan* p, void* base, int B)
 	ws.s2_hist = (double*)(b + p->off_s2hist);
 	ws.ring_v = (double*)(b + p->off_ringv);
 	ws.sbmin = (float*)(b + p->off_sbmin);
+	ws.sblow = (float*)(b + p->off_sblow);
 	return ws;
 }
 
@@ -183,7 +185,8 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 		for (int k = 0; k < nrings; ++k) ring_ptr[k + 1] = ring_ptr[k] + count[k];
 		ring_pix.resize(ring_ptr[nrings]);
 		std::vector<int> fill(ring_ptr.begin(), ring_ptr.end() - 1);
-		for (size_t i = 0; i < rid.size(); ++i) if (rid[i] >= 0) ring_pix[fill[rid[i]]++] = (int)i;
+		// ring pixels are stored as (y << 16) | x, row-major within a ring
+		for (size_t i = 0; i < rid.size(); ++i) if (rid[i] >= 0) ring_pix[fill[rid[i]]++] = (int)(((i / W) << 16) | (i % W));
 		P.nringpix = (int)ring_pix.size();
 		// meshes that reach beyond the first ring centre see a non-constant radial component
 		const double c0 = host_edge(radial_cutoff, radial_pixel_step, 1) - radial_pixel_step / 2;

@@ -26,7 +26,7 @@ struct PlanDev {
 	int n_nonflat;              // tiles with max(r) > first ring centre
 	// device tables
 	const int* ring_ptr;        // [nrings + 1] CSR offsets into ring_pix
-	const int* ring_pix;        // [nringpix] linear pixel index y*W + x, row-major within a ring
+	const int* ring_pix;        // [nringpix] (y << 16) | x, row-major within a ring
 	const int* nonflat_tiles;   // [n_nonflat] tile ids
 	const int* tile_slot;       // [ntiles] index into nonflat list or -1 (flat tile)
 	const double* zoom_w;       // [64][4] cubic B-spline weights per sub-tile phase
@@ -74,6 +74,7 @@ struct Workspace {
 	double* s2_hist;        // [B][rounds][nrings] smoothed ring values per round (diagnostics)
 	double* ring_v;         // [B][nringpix] ring samples (NaN = masked)
 	float* sbmin;           // [B][ntiles][64] minimum valid pixel of every 8x8 sub-block (+inf = none)
+	float* sblow;           // [B][ntiles][64] lower bound of min(x - sq) per sub-block (zeropoint pruning)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -257,81 +257,132 @@ __global__ void __launch_bounds__(TBK_NT) k_zp_min(PlanDev P, Workspace ws,
 //     xmin - (sq0 + slack)  <=  min over the sub-block of (x - sq)  <=  xmin - (sq0 - slack).
 // Pass 1 takes the smallest upper bound over the FFI; pass 2 evaluates exactly only the sub-blocks whose
 // lower bound does not exceed it -- the true minimiser is always among them.
-__device__ __forceinline__ double sm_max_bound(const FfiCtl& c) { return c.mesh_max; }
-
-struct ZpSmem {
-	ZoomTile z;
-	RedSmem red;
-	double slack;
+// One warp per mesh (8 meshes per CTA); lane l owns sub-blocks l and l + 32.
+#define ZP_WARPS 8
+struct ZpWarpSmem {
+	double c[5][5];
+	double wc[8][4];   // zoom weights of the 8 sub-block sample phases (pixel 8a + 4)
 };
 
-__device__ __forceinline__ void zp_setup(ZpSmem& sm, const PlanDev& P, const Workspace& ws, const FfiCtl& c, int tile, int b)
+// sq at the sample pixel of sub-block sbk and the Lipschitz slack of the mesh (warp-uniform)
+__device__ __forceinline__ void zp_mesh_setup(ZpWarpSmem& sm, const PlanDev& P, const double* __restrict__ coef,
+	const FfiCtl& c, int tile, int lane, double& slack)
 {
 	const int ty = tile / P.nx, tx = tile % P.nx;
-	zoom_tile_load(sm.z, ws.coef + (size_t)b * P.ntiles, ty, tx, P.ny, P.nx);
-	zoom_tile_stage(sm.z, c, P.zoom_w);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		double gx = 0.0, gy = 0.0;
-		for (int r = 0; r < 5; ++r) for (int k = 0; k < 4; ++k) {
-			gx = fmax(gx, fabs(sm.z.c[r][k + 1] - sm.z.c[r][k]));
-			gy = fmax(gy, fabs(sm.z.c[k + 1][r] - sm.z.c[k][r]));
-		}
-		sm.slack = sm.z.mesh_const ? 0.0 : (4.0 * (gx + gy) / 64.0) * (1.0 + 1e-9) + 1e-9;
-	}
-	__syncthreads();
+	if (lane < 25) sm.c[lane / 5][lane % 5] = coef[reflect_fold(ty - 2 + lane / 5, P.ny) * P.nx + reflect_fold(tx - 2 + lane % 5, P.nx)];
+	sm.wc[lane >> 2][lane & 3] = __ldg(P.zoom_w + 4 * (8 * (lane >> 2) + 4) + (lane & 3));
+	__syncwarp();
+	double g = 0.0;
+	if (lane < 20) g = fabs(sm.c[lane / 4][lane % 4 + 1] - sm.c[lane / 4][lane % 4]);          // x differences
+	double gx = g;
+	for (int o = 16; o > 0; o >>= 1) gx = fmax(gx, __shfl_xor_sync(0xffffffffu, gx, o));
+	g = 0.0;
+	if (lane < 20) g = fabs(sm.c[lane % 4 + 1][lane / 4] - sm.c[lane % 4][lane / 4]);          // y differences
+	double gy = g;
+	for (int o = 16; o > 0; o >>= 1) gy = fmax(gy, __shfl_xor_sync(0xffffffffu, gy, o));
+	slack = c.mesh_const ? 0.0 : (4.0 * (gx + gy) / 64.0) * (1.0 + 1e-9) + 1e-9;
 }
 
-__global__ void __launch_bounds__(64) k_zp_bound(PlanDev P, Workspace ws)
+__device__ __forceinline__ double zp_sample_sq(const ZpWarpSmem& sm, const FfiCtl& c, int sbk)
 {
-	__shared__ ZpSmem sm;
-	const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
-	FfiCtl& c = ws.ctl[b];
-	if (c.all_masked || c.no_good_mesh) return;
-	zp_setup(sm, P, ws, c, tile, b);
-	const float xmin = ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + t];
-	double ub = INFINITY, dmy = 0.0; int cnt = 0;
-	if (xmin < INFINITY) {
-		const double sq0 = zoom_clip_s(sm.z, zoom_eval(sm.z, sm.z.w, 8 * (t >> 3) + 4, 8 * (t & 7) + 4));
-		ub = (double)xmin - (sq0 - sm.slack);
+	const int a = sbk >> 3, bcol = sbk & 7;   // sample pixel (8a + 4, 8 bcol + 4): first half of the mesh iff a < 4
+	const int oy = a >> 2, ox = bcol >> 2;
+	double acc = 0.0;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		double ra = 0.0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) ra += sm.wc[bcol][j] * sm.c[oy + i][ox + j];
+		acc += sm.wc[a][i] * ra;
 	}
-	block_sum_min_max(sm.red, cnt, ub, dmy);
-	if (t == 0 && ub < INFINITY) atomicMin(&c.min_ub, dkey(ub));
+	if (c.mesh_const) return c.mesh_min;
+	return fmin(fmax(acc, c.mesh_min), c.mesh_max);
 }
 
-__global__ void __launch_bounds__(64) k_zp_exact(PlanDev P, Workspace ws,
+// pass 1: per sub-block bounds; the lower bounds are kept (rounded down to float32) for pass 2
+__global__ void __launch_bounds__(32 * ZP_WARPS) k_zp_bound(PlanDev P, Workspace ws)
+{
+	__shared__ ZpWarpSmem smw[ZP_WARPS];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int tile = blockIdx.x * ZP_WARPS + w, b = blockIdx.y;
+	FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh || tile >= P.ntiles) return;
+	double slack;
+	zp_mesh_setup(smw[w], P, ws.coef + (size_t)b * P.ntiles, c, tile, lane, slack);
+	float* sb = ws.sbmin + ((size_t)b * P.ntiles + tile) * 64;
+	float* lb = ws.sblow + ((size_t)b * P.ntiles + tile) * 64;
+	double ub = INFINITY;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const int sbk = lane + 32 * h;
+		const float xmin = sb[sbk];
+		float low = INFINITY;
+		if (xmin < INFINITY) {
+			const double sq0 = zp_sample_sq(smw[w], c, sbk);
+			ub = fmin(ub, (double)xmin - (sq0 - slack));
+			low = __double2float_rd((double)xmin - (sq0 + slack));
+		}
+		lb[sbk] = low;
+	}
+	for (int o = 16; o > 0; o >>= 1) ub = fmin(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+	if (lane == 0 && ub < INFINITY) atomicMin(&c.min_ub, dkey(ub));
+}
+
+// pass 2: exact evaluation of the candidate sub-blocks (lower bound <= smallest upper bound)
+__global__ void __launch_bounds__(32 * ZP_WARPS) k_zp_exact(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
 {
-	__shared__ ZpSmem sm;
-	const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+	__shared__ ZpWarpSmem smw[ZP_WARPS];
+	__shared__ double wT[4][64];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int tile = blockIdx.x * ZP_WARPS + w, b = blockIdx.y;
 	FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
-	// cheap reject of the whole mesh: its smallest pixel against the coarsest bound
-	const float xmin = ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + t];
 	const double U = dkey_inv(c.min_ub);
-	if (__syncthreads_and(!((double)xmin - sm_max_bound(c) <= U))) return;
-	zp_setup(sm, P, ws, c, tile, b);
+	unsigned cand[2] = {0u, 0u};
+	if (tile < P.ntiles) {
+		const float* lb = ws.sblow + ((size_t)b * P.ntiles + tile) * 64;
+		cand[0] = __ballot_sync(0xffffffffu, (double)lb[lane] <= U);
+		cand[1] = __ballot_sync(0xffffffffu, (double)lb[lane + 32] <= U);
+	}
+	if (!__syncthreads_or(cand[0] | cand[1])) return;
+	wT[threadIdx.x & 3][threadIdx.x >> 2] = __ldg(P.zoom_w + threadIdx.x);
+	__syncthreads();
+	if (!(cand[0] | cand[1])) return;
+	double slack;
+	zp_mesh_setup(smw[w], P, ws.coef + (size_t)b * P.ntiles, c, tile, lane, slack);
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	const size_t img = (size_t)b * P.H * P.W;
 	double mn = INFINITY;
-	if (xmin < INFINITY) {
-		const int r0 = 8 * (t >> 3), c0 = 8 * (t & 7);
-		const double sq0 = zoom_clip_s(sm.z, zoom_eval(sm.z, sm.z.w, r0 + 4, c0 + 4));
-		if ((double)xmin - (sq0 + sm.slack) <= U) {
-			const int ty = tile / P.nx, tx = tile % P.nx;
-			const size_t img = (size_t)b * P.H * P.W;
-			for (int i = 0; i < 8; ++i) {
-				const size_t off = img + (size_t)(ty * TBK_TILE + r0 + i) * P.W + tx * TBK_TILE + c0;
-				const float4 xa = __ldg(reinterpret_cast<const float4*>(cube + off)), xb = __ldg(reinterpret_cast<const float4*>(cube + off + 4));
-				const uchar4 ma = __ldg(reinterpret_cast<const uchar4*>(mask + off)), mb = __ldg(reinterpret_cast<const uchar4*>(mask + off + 4));
-				const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-				const unsigned char ms[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-				for (int j = 0; j < 8; ++j)
-					if (!ms[j]) mn = fmin(mn, (double)xs[j] - zoom_clip_s(sm.z, zoom_eval(sm.z, sm.z.w, r0 + i, c0 + j)));
+	for (int h = 0; h < 2; ++h) {
+		unsigned m = cand[h];
+		while (m) {
+			const int sbk = 32 * h + __ffs(m) - 1;
+			m &= m - 1;
+			const int r0 = 8 * (sbk >> 3), c0 = 8 * (sbk & 7);
+			// 64 pixels of the sub-block, two per lane
+#pragma unroll
+			for (int e = 0; e < 2; ++e) {
+				const int lr = r0 + ((lane + 32 * e) >> 3), lc = c0 + ((lane + 32 * e) & 7);
+				const size_t off = img + (size_t)(ty * TBK_TILE + lr) * P.W + tx * TBK_TILE + lc;
+				if (!__ldg(mask + off)) {
+					const int oy = lr >> 5, ox = lc >> 5;
+					double acc = 0.0;
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						double ra = 0.0;
+#pragma unroll
+						for (int j = 0; j < 4; ++j) ra += wT[j][lc] * smw[w].c[oy + i][ox + j];
+						acc += wT[i][lr] * ra;
+					}
+					const double sq = c.mesh_const ? c.mesh_min : fmin(fmax(acc, c.mesh_min), c.mesh_max);
+					mn = fmin(mn, (double)__ldg(cube + off) - sq);
+				}
 			}
 		}
 	}
-	double dmy = 0.0; int cnt = 0;
-	block_sum_min_max(sm.red, cnt, mn, dmy);
-	if (t == 0 && mn < INFINITY) atomicMin(&c.min_key, dkey(mn));
+	for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+	if (lane == 0 && mn < INFINITY) atomicMin(&c.min_key, dkey(mn));
 }
 
 __global__ void k_set_zp(Workspace ws, int B)
@@ -356,8 +407,9 @@ __global__ void k_ring_gather(PlanDev P, Workspace ws, const float* __restrict__
 	if (i >= P.nringpix) return;
 	const FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
-	const int pix = __ldg(P.ring_pix + i);
-	const size_t off = (size_t)b * P.H * P.W + pix;
+	const unsigned yx = (unsigned)__ldg(P.ring_pix + i);
+	const int py = (int)(yx >> 16), px = (int)(yx & 0xFFFFu);
+	const size_t off = (size_t)b * P.H * P.W + (size_t)py * P.W + px;
 	double val = nan_d();
 	if (!__ldg(mask + off)) {
 		const float x = __ldg(cube + off);
@@ -365,8 +417,7 @@ __global__ void k_ring_gather(PlanDev P, Workspace ws, const float* __restrict__
 			const float s = (x + 0.0f) + (float)c.zp;
 			val = (double)(float)log10((double)s);
 		} else {
-			const int y = pix / P.W, xx = pix % P.W;
-			const double sq = zoom_clip(c, zoom_eval_global(ws.coef + (size_t)b * P.ntiles, P.zoom_w, y, xx, P.ny, P.nx));
+			const double sq = zoom_clip(c, zoom_eval_global(ws.coef + (size_t)b * P.ntiles, P.zoom_w, py, px, P.ny, P.nx));
 			val = log10(((double)x - sq) + c.zp);
 		}
 	}
@@ -1119,8 +1170,9 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 			if (round > 0) {
 				if (tile_kernel == 0) LAUNCH(TBK_K_ZP_MIN, (k_zp_min<<<gt, TBK_NT, 0, st>>>(P, ws, cube, mask)));
 				else {
-					LAUNCH(TBK_K_ZP_MIN, (k_zp_bound<<<gt, 64, 0, st>>>(P, ws)));
-					LAUNCH(TBK_K_ZP_MIN, (k_zp_exact<<<gt, 64, 0, st>>>(P, ws, cube, mask)));
+					const dim3 gz((P.ntiles + ZP_WARPS - 1) / ZP_WARPS, B);
+					LAUNCH(TBK_K_ZP_MIN, (k_zp_bound<<<gz, 32 * ZP_WARPS, 0, st>>>(P, ws)));
+					LAUNCH(TBK_K_ZP_MIN, (k_zp_exact<<<gz, 32 * ZP_WARPS, 0, st>>>(P, ws, cube, mask)));
 				}
 				LAUNCH(TBK_K_MISC, (k_set_zp<<<gb, 128, 0, st>>>(ws, B)));
 			}

@@ -97,13 +97,14 @@ __device__ __forceinline__ double zoom_eval_global(const double* __restrict__ co
 	const int sy = ty - 2 + (lrow >> 5), sx = tx - 2 + (lcol >> 5);
 	const double* wy = zw + 4 * lrow;
 	const double* wx = zw + 4 * lcol;
+	const bool interior = sy >= 0 && sy + 3 < ny && sx >= 0 && sx + 3 < nx;
 	int cx[4];
 #pragma unroll
-	for (int b = 0; b < 4; ++b) cx[b] = reflect_fold(sx + b, nx);
+	for (int b = 0; b < 4; ++b) cx[b] = interior ? sx + b : reflect_fold(sx + b, nx);
 	double acc = 0.0;
 #pragma unroll
 	for (int a = 0; a < 4; ++a) {
-		const double* row = coef + reflect_fold(sy + a, ny) * nx;
+		const double* row = coef + (interior ? sy + a : reflect_fold(sy + a, ny)) * nx;
 		double ra = 0.0;
 #pragma unroll
 		for (int b = 0; b < 4; ++b) ra += wx[b] * row[cx[b]];
