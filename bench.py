@@ -191,9 +191,7 @@ def run_b200(args):
 	lib = _lib.load()
 
 	def step():
-		for a in range(0, n, chunk):
-			b = min(a + chunk, n)
-			fit.fit(cube[a:b], meta_d[a * isz:b * isz], bkg_out=bkg[a:b], mask_out=mask[a:b])
+		fit.fit_stack(cube, meta_d, bkg, mask, chunk=chunk, nstreams=args.streams)
 
 	def barrier():
 		torch.cuda.synchronize(dev)
@@ -318,7 +316,7 @@ def run_b200(args):
 		"steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
 		"scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
 		"config": {"workload": "synthetic single CCD 2048x2048 x 1,340 FFIs (30-min cadence sector), TESS path camera 1 ccd 2, 3 rounds",
-			"ffis_per_gpu": n, "ffis_per_launch": chunk, "l2": "inputs (22.5 GB/GPU) larger than L2", "parallelism": f"cadence shards x{world}"},
+			"ffis_per_gpu": n, "ffis_per_launch": chunk, "streams": args.streams, "l2": "inputs (22.5 GB/GPU) larger than L2", "parallelism": f"cadence shards x{world}"},
 		"roofline": roofline, "cpu_baseline": cpu,
 		"e2e": {"value": e2e_value, "unit": "FFIs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
 			"note": f"pinned host sample of {ne} FFIs cycled {reps}x per step; results (bkg f32 + mask u8) copied back"},
@@ -337,7 +335,8 @@ def main():
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--ffis', type=int, default=1340, help='FFIs per GPU per step')
-	ap.add_argument('--chunk', type=int, default=64, help='FFIs per tbk_fit_batch launch')
+	ap.add_argument('--chunk', type=int, default=32, help='FFIs per tbk_fit_batch launch')
+	ap.add_argument('--streams', type=int, default=2, help='CUDA streams the chunks alternate between')
 	ap.add_argument('--e2e-ffis', type=int, default=128, help='pinned host sample size for the end-to-end leg')
 	ap.add_argument('--prepare-ffis', type=int, default=256)
 	ap.add_argument('--no-prepare', dest='prepare', action='store_false')

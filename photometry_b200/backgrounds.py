@@ -86,21 +86,46 @@ class BackgroundFitter:
 			pass
 
 	# ------------------------------------------------------------------------------------------
-	def workspace(self, B):
-		ws = self._ws.get(B)
+	def workspace(self, B, slot=0):
+		"""Scratch buffer for a batch of B; ``slot`` selects independent buffers for concurrent streams."""
+		ws = self._ws.get((B, slot))
 		if ws is None:
 			nbytes = self.lib.tbk_workspace_bytes(self._plan, B)
 			ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
 			off = (-ws.data_ptr()) % 256
 			ws = ws[off:off + nbytes]
-			self._ws[B] = ws
+			self._ws[(B, slot)] = ws
 		return ws
+
+	def fit_stack(self, cube, meta, bkg_out, mask_out, chunk=64, extra_mask=None, status_out=None, nstreams=2):
+		"""
+		Fit a whole device-resident stack in chunks of ``chunk`` FFIs, alternating between ``nstreams`` CUDA
+		streams (each with its own scratch) so that the small latency-bound kernels of one chunk overlap the
+		throughput kernels of another.  The current stream waits for all of them at the end.
+		"""
+		n = cube.shape[0]
+		meta_d = meta if isinstance(meta, torch.Tensor) else self.meta_to_device(meta)
+		isz, ssz = META_DTYPE.itemsize, STATUS_DTYPE.itemsize
+		cur = torch.cuda.current_stream(self.device)
+		if not hasattr(self, '_streams') or len(self._streams) < nstreams:
+			self._streams = [torch.cuda.Stream(self.device) for _ in range(nstreams)]
+		for s in self._streams[:nstreams]:
+			s.wait_stream(cur)
+		for idx, a in enumerate(range(0, n, chunk)):
+			b = min(a + chunk, n)
+			k = idx % nstreams
+			with torch.cuda.stream(self._streams[k]):
+				self.fit(cube[a:b], meta_d[a * isz:b * isz], None if extra_mask is None else extra_mask[a:b],
+					bkg_out=bkg_out[a:b], mask_out=mask_out[a:b],
+					status_out=None if status_out is None else status_out[a * ssz:b * ssz], slot=k)
+		for s in self._streams[:nstreams]:
+			cur.wait_stream(s)
 
 	def meta_to_device(self, meta):
 		meta = np.ascontiguousarray(meta, dtype=META_DTYPE)
 		return torch.from_numpy(meta.view(np.uint8).copy()).to(self.device, non_blocking=True)
 
-	def fit(self, cube, meta=None, extra_mask=None, bkg_out=None, mask_out=None, status_out=None, profile=None):
+	def fit(self, cube, meta=None, extra_mask=None, bkg_out=None, mask_out=None, status_out=None, profile=None, slot=0):
 		"""
 		Fit a device-resident batch.  ``cube`` float32 cuda tensor [B, H, W]; ``meta`` a
 		``tbk_ffi_meta`` numpy array or an already uploaded uint8 tensor; ``extra_mask`` optional
@@ -124,7 +149,7 @@ class BackgroundFitter:
 		bkg = bkg_out if bkg_out is not None else torch.empty_like(cube)
 		mask = mask_out if mask_out is not None else torch.empty(cube.shape, dtype=torch.uint8, device=self.device)
 		status = status_out if status_out is not None else torch.empty(B * STATUS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
-		ws = self.workspace(B)
+		ws = self.workspace(B, slot)
 		stream = torch.cuda.current_stream(self.device).cuda_stream
 		if profile is not None:
 			# measurement aid: synchronising variant that returns ms per kernel class in ``profile`` (dict)
