@@ -192,6 +192,95 @@ __global__ void __launch_bounds__(32, TW_MINB) k_tile_base_warp(PlanDev P, Works
 	if (lane == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
 
+// K_tile_base_w2: the same work as k_tile_base_warp with two warps per mesh (64 keys per thread): half the
+// registers per thread, so twice the warps per SM to hide the latencies of the bucketing passes.
+// Thread t, load i (0..15) owns row 4i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3.
+#ifndef TW2_MINB
+#define TW2_MINB 10
+#endif
+template <bool HAS_EXTRA>
+__global__ void __launch_bounds__(64, TW2_MINB) k_tile_base_w2(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
+{
+	__shared__ TwBlockSmem<TwF32, 2> sm;
+	__shared__ uint32_t s_sb[64];
+	__shared__ int s_nbad, s_nz;
+	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	FfiCtl& c = ws.ctl[b];
+	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
+	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + 2 * w + (lane >> 4)) * P.W + gx;
+	const size_t step = (size_t)4 * P.W;
+	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
+	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
+	s_sb[tid] = TW_INVALID;
+	if (tid == 0) { s_nbad = 0; s_nz = 0; }
+
+	uint32_t v[64];
+	{
+		const float* p = cube + base;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			const float4 r = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * step));
+			v[4 * i] = __float_as_uint(r.x + 0.0f); v[4 * i + 1] = __float_as_uint(r.y + 0.0f);
+			v[4 * i + 2] = __float_as_uint(r.z + 0.0f); v[4 * i + 3] = __float_as_uint(r.w + 0.0f);
+		}
+	}
+	uint32_t nz = 0u, sb[8];
+	int nbad = 0;
+#pragma unroll
+	for (int a = 0; a < 8; ++a) sb[a] = TW_INVALID;
+#pragma unroll
+	for (int i = 0; i < 16; ++i) {
+		const size_t off = base + (size_t)i * step;
+		uint32_t ex = 0u;
+		if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
+		uint32_t m = 0u;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const uint32_t k = v[4 * i + q];
+			nz |= k;
+			bool ok = k <= cut;
+			if (excl) ok = false;
+			if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
+			m |= ok ? 0u : (1u << (8 * q));
+			const uint32_t kv = ok ? k : TW_INVALID;
+			v[4 * i + q] = kv;
+			sb[i >> 1] = min(sb[i >> 1], kv);   // rows 8a .. 8a+7 are loads 2a, 2a+1 of both warps
+		}
+		nbad += __popc(m);
+		*reinterpret_cast<unsigned int*>(mask_out + off) = m;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int a = 0; a < 8; ++a) {
+		uint32_t t = sb[a];
+		t = min(t, __shfl_xor_sync(0xffffffffu, t, 1));
+		t = min(t, __shfl_xor_sync(0xffffffffu, t, 16));
+		if ((lane & 17) == 0) atomicMin(&s_sb[a * 8 + (lane >> 1)], t);
+	}
+	nbad = __reduce_add_sync(0xffffffffu, nbad);
+	nz = __reduce_or_sync(0xffffffffu, nz);
+	if (lane == 0) { atomicAdd(&s_nbad, nbad); if (nz) atomicOr(&s_nz, 1); }
+	__syncthreads();
+	const uint32_t mysb = s_sb[tid];
+	ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + tid] = __uint_as_float(mysb);
+	if (tid == 0) {
+		const int n = 4096 - s_nbad;
+		if (s_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+		if (n > 0) atomicAdd(&c.n_valid, n);
+	}
+	if (w == 0) {
+		uint32_t kmin = min(mysb, s_sb[tid + 32]);
+		kmin = __reduce_min_sync(0xffffffffu, kmin);
+		if (lane == 0 && kmin != TW_INVALID) atomicMin(&c.min_bits, kmin);
+	}
+	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
+	TileStat st; bool writer;
+	tile_block_stats<TwF32, 2, 64>(v, sm, st, writer);
+	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+}
+
 // K_post_base: all-zero rule (pixel_flags.py:54-56), all-masked early-out (backgrounds.py:101-102),
 // zeropoint of round 1 (backgrounds.py:171).
 __global__ void k_post_base(PlanDev P, Workspace ws, tbk_ffi_status* status, int B)
@@ -850,10 +939,13 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
 
 // K_tile_round_w: same result as k_tile_round with the bucketed algorithm of tbk_tile_warp.cuh on float64
 // residuals.  128 threads per mesh; thread t, load i (0..7) owns row 8i + 2(t/32) + (t%32)/16, columns 4(t%16)..+3.
-__global__ void __launch_bounds__(128) k_tile_round_w(PlanDev P, Workspace ws,
+#ifndef TWR_MINB
+#define TWR_MINB 4
+#endif
+__global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
 {
-	__shared__ TileRound64Smem sm;
+	__shared__ TwBlockSmem<TwF64, 4> sm;
 	__shared__ RadialSmem2 rs;
 	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
 	const FfiCtl& c = ws.ctl[b];
@@ -880,7 +972,7 @@ __global__ void __launch_bounds__(128) k_tile_round_w(PlanDev P, Workspace ws,
 		}
 	}
 	TileStat st; bool writer;
-	tile_block_stats64(key, sm, st, writer);
+	tile_block_stats<TwF64, 4, 32>(key, sm, st, writer);
 	if (writer) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
 }
 
@@ -1160,6 +1252,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	const int gb = (B + 127) / 128;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
 	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 2 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 2) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<true><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
 	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<false><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
 	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));

@@ -59,6 +59,17 @@ struct TwF32 {
 		return max(0, min(TW_NB - 1, b));
 	}
 	// smallest float32 >= d / largest float32 <= d as keys (exact translation of a float64 bound)
+	__device__ static __forceinline__ Map make_map(double w0d, double w1d)
+	{
+		const float w0 = (float)w0d, w1 = (float)w1d;
+		Map bm;
+		bm.scale = (float)(TW_NB - 2) / (w1 - w0);
+		if (!(bm.scale < 1e30f)) bm.scale = 1e30f;
+		if (w0 > 0.f && w0 * bm.scale > 4194304.0f) bm.scale = 4194304.0f / w0;  // keeps off >= 2^22
+		bm.off = fmaf(-w0, bm.scale, 8388609.0f);
+		return bm;
+	}
+	__device__ static __forceinline__ double pivot_of(double med) { return (double)fmaxf((float)med, 0.f); }
 	__device__ static __forceinline__ K key_ceil(double d)
 	{
 		if (!(d > 0.0)) return 0u;
@@ -93,6 +104,16 @@ struct TwF64 {
 		const long long b = __double_as_longlong(t) - 0x4330000000000000LL;
 		return (int)max(0LL, min((long long)(TW_NB - 1), b));
 	}
+	__device__ static __forceinline__ Map make_map(double w0, double w1)
+	{
+		Map bm;
+		bm.scale = (double)(TW_NB - 2) / (w1 - w0);
+		if (!(bm.scale < 1e300)) bm.scale = 1e300;
+		bm.lo_c = w0 - 1.5 / bm.scale; bm.hi_c = w1 + 1.5 / bm.scale;
+		bm.off = fma(-w0, bm.scale, 4503599627370497.0);  // 2^52 + 1
+		return bm;
+	}
+	__device__ static __forceinline__ double pivot_of(double med) { return med; }
 	__device__ static __forceinline__ K key_ceil(double d) { return dkey(d); }
 	__device__ static __forceinline__ bool key_floor(double d, K& key) { key = dkey(d); return true; }
 };
@@ -418,35 +439,39 @@ __device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// Float64 residuals (x - radial): one CTA of 128 threads per mesh, 32 values per thread.  The four warps
-// share the counters / key buffer for the two passes; warp 0 alone runs the iterations.
-struct TileRound64Smem {
-	TwSmem<unsigned long long> tw;
-	TwBinMap64 bm;
+// Block version: NW warps share one mesh (VPT = 4096 / (32 NW) keys per thread in registers).  The warps
+// cooperate on the two bucketing passes and the moment sweep; warp 0 alone runs the iterations.
+// Used with NW = 4 for float64 residuals (x - radial) and NW = 2 for float32 pixels.
+template <typename T, int NW>
+struct TwBlockSmem {
+	TwSmem<typename T::K> tw;
+	typename T::Map bm;
 	double pivot;
-	double red[2][4][3];
-	unsigned long long kmin, kmax;
-	int nvalid, ntl[4], constant;
+	double red[2][NW][2];
+	typename T::K kmin, kmax;
+	int nvalid, ntl[NW], constant;
 };
 
-__device__ void tile_block_stats64(const unsigned long long (&key)[32], TileRound64Smem& sm, TileStat& out, bool& writer)
+template <typename T, int NW, int VPT>
+__device__ void tile_block_stats(const typename T::K (&key)[VPT], TwBlockSmem<T, NW>& sm, TileStat& out, bool& writer)
 {
-	typedef unsigned long long K;
+	typedef typename T::K K;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const K INV = T::invalid();
 	writer = (tid == 0);
 	out.mean = out.med = out.std = nan_d();
 	out.nfin = 0; out.pad = 0;
 	// ---- count, min, max
-	int n = 0; K kmin = ~0ULL, kmax = 0ULL;
+	int n = 0; K kmin = T::padkey(), kmax = 0;
 #pragma unroll
-	for (int e = 0; e < 32; ++e) {
+	for (int e = 0; e < VPT; ++e) {
 		const K k = key[e];
-		if (k != ~0ULL) { ++n; kmin = min(kmin, k); kmax = max(kmax, k); }
+		if (k != INV) { ++n; kmin = min(kmin, k); kmax = max(kmax, k); }
 	}
 	n = __reduce_add_sync(0xffffffffu, n);
 	for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
-	if (tid == 0) { sm.nvalid = 0; sm.kmin = ~0ULL; sm.kmax = 0ULL; sm.constant = 0; }
-	for (int i = tid; i < TW_CNT_WORDS; i += 128) sm.tw.cnt[i] = 0u;
+	if (tid == 0) { sm.nvalid = 0; sm.kmin = T::padkey(); sm.kmax = 0; sm.constant = 0; }
+	for (int i = tid; i < TW_CNT_WORDS; i += 32 * NW) sm.tw.cnt[i] = 0u;
 	__syncthreads();
 	if (lane == 0) { atomicAdd(&sm.nvalid, n); atomicMin(&sm.kmin, kmin); atomicMax(&sm.kmax, kmax); }
 	__syncthreads();
@@ -455,81 +480,85 @@ __device__ void tile_block_stats64(const unsigned long long (&key)[32], TileRoun
 	// ---- robust window from warp 0's samples (its rows are spread over the whole mesh)
 	if (w == 0) {
 		const int sel = lane & 3;
-		const K sa = sel == 0 ? key[0] : sel == 1 ? key[9] : sel == 2 ? key[18] : key[27];
-		const K sb = sel == 0 ? key[14] : sel == 1 ? key[23] : sel == 2 ? key[4] : key[29];
+		const K sa = sel == 0 ? key[0] : sel == 1 ? key[VPT / 4 + 1] : sel == 2 ? key[VPT / 2 + 2] : key[3 * VPT / 4 + 3];
+		const K sb = sel == 0 ? key[VPT / 2 - 2] : sel == 1 ? key[3 * VPT / 4 - 1] : sel == 2 ? key[VPT / 8] : key[VPT - 3];
 		double med = 0.0, iqr = 0.0; int sets = 0;
 #pragma unroll
 		for (int t = 0; t < 2; ++t) {
 			const K k = warp_bitonic32<K>(t ? sb : sa, lane);
-			const int m = __popc(__ballot_sync(0xffffffffu, k != ~0ULL));
+			const int m = __popc(__ballot_sync(0xffffffffu, k != INV));
 			if (m >= 8) {
-				med += dkey_inv(__shfl_sync(0xffffffffu, k, m >> 1));
-				iqr += dkey_inv(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - dkey_inv(__shfl_sync(0xffffffffu, k, m >> 2));
+				med += T::val(__shfl_sync(0xffffffffu, k, m >> 1));
+				iqr += T::val(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - T::val(__shfl_sync(0xffffffffu, k, m >> 2));
 				++sets;
 			}
 		}
 		if (lane == 0) {
 			double w0, w1, pv;
-			const double vmin = dkey_inv(sm.kmin), vmax = dkey_inv(sm.kmax);
+			const double vmin = T::val(sm.kmin), vmax = T::val(sm.kmax);
 			if (sets && iqr > 0.0) {
 				med /= (double)sets;
 				const double half = 10.0 * (iqr / (double)sets) / 1.349;
-				w0 = med - half; w1 = med + half; pv = med;
+				w0 = med - half; w1 = med + half; pv = T::pivot_of(med);
 			} else {
 				w0 = vmin; w1 = vmax; pv = vmin;
 				if (!(vmax > vmin)) sm.constant = 1;
 			}
-			TwBinMap64 bm;
-			bm.scale = (double)(TW_NB - 2) / (w1 - w0);
-			if (!(bm.scale < 1e300)) bm.scale = 1e300;
-			bm.lo_c = w0 - 1.5 / bm.scale; bm.hi_c = w1 + 1.5 / bm.scale;
-			bm.off = fma(-w0, bm.scale, 4503599627370497.0);  // 2^52 + 1
-			sm.bm = bm; sm.pivot = pv;
+			sm.bm = T::make_map(w0, w1); sm.pivot = pv;
 		}
 	}
 	__syncthreads();
-	if (sm.constant) {  // all residuals equal: sigma = 0, nothing is clipped
-		out.mean = out.med = dkey_inv(sm.kmin); out.std = 0.0; out.nfin = nvalid;
+	if (sm.constant) {  // all values equal: sigma = 0, nothing is clipped
+		out.mean = out.med = T::val(sm.kmin); out.std = 0.0; out.nfin = nvalid;
 		return;
 	}
-	const TwBinMap64 bm = sm.bm;
+	const typename T::Map bm = sm.bm;
 	const double pivot = sm.pivot;
 	// ---- pass 1: counts
 #pragma unroll
-	for (int e = 0; e < 32; ++e) {
+	for (int e = 0; e < VPT; ++e) {
 		const K k = key[e];
-		if (k != ~0ULL) { const int b = TwF64::bin(bm, k); atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4)); }
+		const int b = T::bin(bm, k);
+		if (k != INV) atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4));
 	}
 	__syncthreads();
 	if (w == 0) tw_scan_counts(sm.tw.cnt, lane);
 	__syncthreads();
-	// ---- pass 2: scatter
+	// ---- pass 2: scatter in groups of 8
 #pragma unroll
-	for (int e = 0; e < 32; ++e) {
-		const K k = key[e];
-		if (k != ~0ULL) {
-			const int b = TwF64::bin(bm, k);
-			const int sh = (b & 1) << 4;
-			const uint32_t old = atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << sh);
-			sm.tw.keys[(old >> sh) & 0xFFFFu] = k;
+	for (int g = 0; g < VPT / 8; ++g) {
+		uint32_t old[8]; int sh[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const K k = key[8 * g + j];
+			const int b = T::bin(bm, k);
+			sh[j] = (b & 1) << 4;
+			old[j] = 0u;
+			if (k != INV) old[j] = atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << sh[j]);
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const K k = key[8 * g + j];
+			if (k != INV) sm.tw.keys[(old[j] >> sh[j]) & 0xFFFFu] = k;
 		}
 	}
 	__syncthreads();
-	// ---- moments: all four warps sweep the bucketed keys
+	// ---- moments: all warps sweep the bucketed keys
 	const uint32_t t0e = tw_cend(sm.tw.cnt, 0), t1s = tw_cstart(sm.tw.cnt, TW_NB - 1);
 	double c1 = 0.0, c2 = 0.0, q1 = 0.0, q2 = 0.0; int tn = 0;
-	for (uint32_t p = tid; p < (uint32_t)nvalid; p += 128) {
-		const double d = dkey_inv(sm.tw.keys[p]) - pivot;
+	for (uint32_t p = tid; p < (uint32_t)nvalid; p += 32 * NW) {
+		const double d = T::val(sm.tw.keys[p]) - pivot;
 		if (p >= t0e && p < t1s) { c1 += d; c2 = fma(d, d, c2); }
 		else { ++tn; q1 += d; q2 = fma(d, d, q2); }
 	}
-	c1 = warp_sum_d(c1); c2 = warp_sum_d(c2); q1 = warp_sum_d(q1); q2 = warp_sum_d(q2);
+	c1 = warp_sum_d(c1); c2 = warp_sum_d(c2);
 	tn = __reduce_add_sync(0xffffffffu, tn);
+	if (__any_sync(0xffffffffu, tn != 0)) { q1 = warp_sum_d(q1); q2 = warp_sum_d(q2); }
 	if (lane == 0) { sm.red[0][w][0] = c1; sm.red[0][w][1] = c2; sm.red[1][w][0] = q1; sm.red[1][w][1] = q2; sm.ntl[w] = tn; }
 	__syncthreads();
 	if (w != 0) { writer = false; return; }
 	double s1c = 0.0, s2c = 0.0, t1 = 0.0, t2 = 0.0; tn = 0;
 #pragma unroll
-	for (int q = 0; q < 4; ++q) { s1c += sm.red[0][q][0]; s2c += sm.red[0][q][1]; t1 += sm.red[1][q][0]; t2 += sm.red[1][q][1]; tn += sm.ntl[q]; }
-	out = tw_iterate<TwF64>(sm.tw.keys, sm.tw.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
+	for (int q = 0; q < NW; ++q) { s1c += sm.red[0][q][0]; s2c += sm.red[0][q][1]; t1 += sm.red[1][q][0]; t2 += sm.red[1][q][1]; tn += sm.ntl[q]; }
+	out = tw_iterate<T>(sm.tw.keys, sm.tw.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
 }
