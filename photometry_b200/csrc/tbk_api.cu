@@ -147,7 +147,8 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	P.flux_cutoff = (float)flux_cutoff;
 	P.xc = xc; P.yc = yc; P.radial_cutoff = radial_cutoff; P.step = radial_pixel_step;
 
-	std::vector<int> ring_ptr(1, 0), ring_pix, nonflat, tile_slot(P.ntiles, -1);
+	std::vector<int> ring_ptr(1, 0), ring_pix, nonflat, tile_slot(P.ntiles, -1), ringtile_id, ringtile_ptr(1, 0);
+	std::vector<unsigned> ringtile_ent;
 	if (P.use_radial) {
 		// backgrounds.py:145-154
 		std::vector<double> r((size_t)H * W);
@@ -188,6 +189,27 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 		// ring pixels are stored as (y << 16) | x, row-major within a ring
 		for (size_t i = 0; i < rid.size(); ++i) if (rid[i] >= 0) ring_pix[fill[rid[i]]++] = (int)(((i / W) << 16) | (i % W));
 		P.nringpix = (int)ring_pix.size();
+		if (ring_pix.size() >= (1u << 20)) { delete p; tbk_set_error("too many ring pixels (%zu)", ring_pix.size()); return TBK_ERR_INVALID; }
+		// the same pixels grouped by mesh (for the gather kernel, which stages one mesh's spline coefficients)
+		{
+			std::vector<int> tcount(P.ntiles, 0);
+			for (size_t j = 0; j < ring_pix.size(); ++j) {
+				const int y = ring_pix[j] >> 16, x = ring_pix[j] & 0xFFFF;
+				++tcount[(y / TBK_TILE) * P.nx + x / TBK_TILE];
+			}
+			std::vector<int> slot_of(P.ntiles, -1);
+			for (int t = 0; t < P.ntiles; ++t) if (tcount[t]) { slot_of[t] = (int)ringtile_id.size(); ringtile_id.push_back(t); }
+			ringtile_ptr.assign(ringtile_id.size() + 1, 0);
+			for (size_t k = 0; k < ringtile_id.size(); ++k) ringtile_ptr[k + 1] = ringtile_ptr[k] + tcount[ringtile_id[k]];
+			ringtile_ent.resize(ring_pix.size());
+			std::vector<int> fill2(ringtile_ptr.begin(), ringtile_ptr.end() - 1);
+			for (size_t j = 0; j < ring_pix.size(); ++j) {
+				const int y = ring_pix[j] >> 16, x = ring_pix[j] & 0xFFFF;
+				const int t = (y / TBK_TILE) * P.nx + x / TBK_TILE;
+				ringtile_ent[fill2[slot_of[t]]++] = ((unsigned)j << 12) | (unsigned)(((y % TBK_TILE) << 6) | (x % TBK_TILE));
+			}
+			P.n_ringtiles = (int)ringtile_id.size();
+		}
 		// meshes that reach beyond the first ring centre see a non-constant radial component
 		const double c0 = host_edge(radial_cutoff, radial_pixel_step, 1) - radial_pixel_step / 2;
 		for (int t = 0; t < P.ntiles; ++t) {
@@ -220,7 +242,8 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	int rc;
 	if ((rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
 		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
-		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle))) {
+		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle)) ||
+		(rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
 		tbk_plan_destroy(p);
 		return rc;
 	}

@@ -29,6 +29,10 @@ struct PlanDev {
 	const int* ring_pix;        // [nringpix] (y << 16) | x, row-major within a ring
 	const int* nonflat_tiles;   // [n_nonflat] tile ids
 	const int* tile_slot;       // [ntiles] index into nonflat list or -1 (flat tile)
+	int n_ringtiles;            // meshes that contain at least one ring pixel
+	const int* ringtile_id;     // [n_ringtiles] mesh id
+	const int* ringtile_ptr;    // [n_ringtiles + 1] CSR offsets into ringtile_ent
+	const unsigned* ringtile_ent; // [nringpix] (index into the ring-ordered sample array << 12) | (row << 6 | col) within the mesh
 	const double* zoom_w;       // [64][4] cubic B-spline weights per sub-tile phase
 	const double2* twiddle;     // [TBK_KDE_M/2] exp(-2 pi i k / M)
 };

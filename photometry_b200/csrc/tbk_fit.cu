@@ -513,6 +513,58 @@ __global__ void k_ring_gather(PlanDev P, Workspace ws, const float* __restrict__
 	ws.ring_v[(size_t)b * P.nringpix + i] = val;
 }
 
+// K_ring_gather_t: the same samples, pixels grouped by mesh: one CTA stages the mesh's 5x5 spline
+// coefficients and the weight table once and evaluates its ring pixels from shared memory.
+__global__ void __launch_bounds__(256) k_ring_gather_t(PlanDev P, Workspace ws, const float* __restrict__ cube,
+	const uint8_t* __restrict__ mask, int round)
+{
+	__shared__ double sc[5][6];
+	__shared__ double wT[4][64];
+	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int tile = P.ringtile_id[slot];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	if (round > 0) {
+		const double* coef = ws.coef + (size_t)b * P.ntiles;
+		if (tid < 25) sc[tid / 5][tid % 5] = coef[reflect_fold(ty - 2 + tid / 5, P.ny) * P.nx + reflect_fold(tx - 2 + tid % 5, P.nx)];
+		wT[tid & 3][tid >> 2] = __ldg(P.zoom_w + tid);
+		__syncthreads();
+	}
+	const double zp = c.zp, mmin = c.mesh_min, mmax = c.mesh_max;
+	const float zp32 = (float)c.zp;
+	const int mconst = c.mesh_const;
+	const size_t img = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE;
+	double* __restrict__ dst = ws.ring_v + (size_t)b * P.nringpix;
+	const int lo = P.ringtile_ptr[slot], hi = P.ringtile_ptr[slot + 1];
+	for (int i = lo + tid; i < hi; i += 256) {
+		const unsigned ent = __ldg(P.ringtile_ent + i);
+		const int lr = (ent >> 6) & 63, lc = ent & 63;
+		const size_t off = img + (size_t)lr * P.W + lc;
+		double val = nan_d();
+		if (!__ldg(mask + off)) {
+			const float x = __ldg(cube + off);
+			if (round == 0) {
+				const float s = (x + 0.0f) + zp32;
+				val = (double)(float)log10((double)s);
+			} else {
+				const int oy = lr >> 5, ox = lc >> 5;
+				double acc = 0.0;
+#pragma unroll
+				for (int a = 0; a < 4; ++a) {
+					double ra = 0.0;
+#pragma unroll
+					for (int q = 0; q < 4; ++q) ra += wT[q][lc] * sc[oy + a][ox + q];
+					acc += wT[a][lr] * ra;
+				}
+				const double sq = mconst ? mmin : fmin(fmax(acc, mmin), mmax);
+				val = log10(((double)x - sq) + zp);
+			}
+		}
+		dst[ent >> 12] = val;
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // K_ring_kde: mode of a Gaussian FFT-KDE per ring (backgrounds.py:21-33 + statsmodels 0.13.2
 // KDEUnivariate.fit(gridsize=2000); see oracle/backgrounds_oracle.py:kde_density).
@@ -1270,7 +1322,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 				}
 				LAUNCH(TBK_K_MISC, (k_set_zp<<<gb, 128, 0, st>>>(ws, B)));
 			}
-			LAUNCH(TBK_K_RING_GATHER, (k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round)));
+			if (tile_kernel == 0) LAUNCH(TBK_K_RING_GATHER, (k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round)));
+			else LAUNCH(TBK_K_RING_GATHER, (k_ring_gather_t<<<dim3(P.n_ringtiles, B), 256, 0, st>>>(P, ws, cube, mask, round)));
 			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
 			LAUNCH(TBK_K_RADIAL_FIT, (k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B)));
 			if (P.n_nonflat > 0)
