@@ -581,24 +581,44 @@ struct KdeSmem {
 	int qbin[4], qexcl[4], qcnt[4], qn[4];
 };
 
-__device__ __forceinline__ void kde_fft(double2* x, const double2* __restrict__ tw, bool inverse)
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// exp(-2 pi i q / 2048) (conjugated for the inverse transform) from the 1024-entry table
+template <bool INV>
+__device__ __forceinline__ double2 kde_tw(const double2* __restrict__ tw, int q)
 {
-	// iterative radix-2 DIT on bit-reversed input; M = 2048, blockDim = 512
-	const int tid = threadIdx.x, nt = blockDim.x;
-	for (int s = 1; s <= 11; ++s) {
-		const int half = 1 << (s - 1);
-		const int tstep = TBK_KDE_M >> s;
-		for (int idx = tid; idx < TBK_KDE_M / 2; idx += nt) {
-			const int j = idx & (half - 1);
-			const int k = ((idx >> (s - 1)) << s) + j;
-			double2 w = __ldg(tw + j * tstep);
-			if (inverse) w.y = -w.y;
-			const double2 u = x[k], t = x[k + half];
-			const double2 wt = make_double2(w.x * t.x - w.y * t.y, w.x * t.y + w.y * t.x);
-			x[k] = make_double2(u.x + wt.x, u.y + wt.y);
-			x[k + half] = make_double2(u.x - wt.x, u.y - wt.y);
+	q &= TBK_KDE_M - 1;
+	double2 w = __ldg(tw + (q & (TBK_KDE_M / 2 - 1)));
+	if (q >= TBK_KDE_M / 2) { w.x = -w.x; w.y = -w.y; }
+	if (INV) w.y = -w.y;
+	return w;
+}
+
+// 1024-point complex FFT, Stockham autosort radix-4: 5 stages, 256 butterflies each, natural order in and out.
+// Input in a[], result in b[] (a is used as scratch).  Unnormalised; call with all threads of the CTA.
+template <bool INV>
+__device__ __forceinline__ void kde_fft1024(double2* a, double2* b, const double2* __restrict__ tw)
+{
+	const int i = threadIdx.x;
+	double2* x = a; double2* y = b;
+#pragma unroll
+	for (int p = 1; p < 1024; p <<= 2) {
+		if (i < 256) {
+			const int k = i & (p - 1), j = ((i - k) << 2) + k, q = k * (512 / p);
+			const double2 u0 = x[i];
+			const double2 u1 = cmul(x[i + 256], kde_tw<INV>(tw, q));
+			const double2 u2 = cmul(x[i + 512], kde_tw<INV>(tw, 2 * q));
+			const double2 u3 = cmul(x[i + 768], kde_tw<INV>(tw, 3 * q));
+			const double2 v0 = make_double2(u0.x + u2.x, u0.y + u2.y), v1 = make_double2(u0.x - u2.x, u0.y - u2.y);
+			const double2 v2 = make_double2(u1.x + u3.x, u1.y + u3.y), d = make_double2(u1.x - u3.x, u1.y - u3.y);
+			const double2 v3 = INV ? make_double2(-d.y, d.x) : make_double2(d.y, -d.x);   // (+i) d or (-i) d
+			y[j] = make_double2(v0.x + v2.x, v0.y + v2.y);
+			y[j + p] = make_double2(v1.x + v3.x, v1.y + v3.y);
+			y[j + 2 * p] = make_double2(v0.x - v2.x, v0.y - v2.y);
+			y[j + 3 * p] = make_double2(v1.x - v3.x, v1.y - v3.y);
 		}
 		__syncthreads();
+		double2* t = x; x = y; y = t;
 	}
 }
 
@@ -617,15 +637,14 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 		for (int i = lo + tid; i < hi; i += nt) { const double d = v[i]; if (d == d) f(d); }
 	};
 
-	int n = 0; double mn = INFINITY, mx = -INFINITY;
-	each([&](double d) { ++n; mn = fmin(mn, d); mx = fmax(mx, d); });
+	int n = 0; double mn = INFINITY, mx = -INFINITY, s1 = 0.0, dmy = 0.0;
+	each([&](double d) { ++n; mn = fmin(mn, d); mx = fmax(mx, d); s1 += d; });
+	int nd = 0;
 	block_sum_min_max(sm.red, n, mn, mx);
+	block_sum3(sm.red, nd, s1, dmy);
 	if (n <= 1) { if (tid == 0) *out = nan_d(); return; }  // reduce_mode([]) = NaN; one sample -> NaN
 
 	// std(ddof=1), two-pass like numpy
-	int nd = 0; double s1 = 0.0, dmy = 0.0;
-	each([&](double d) { s1 += d; });
-	block_sum3(sm.red, nd, s1, dmy);
 	const double mean = s1 / (double)n;
 	double ss = 0.0; dmy = 0.0; nd = 0;
 	each([&](double d) { const double e = d - mean; ss += e * e; });
@@ -778,38 +797,66 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 		for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
 		__syncthreads();
 	}
-	// bit-reversal permutation + normalisation binned = g / (delta * nobs)
-	const double norm = 1.0 / (delta * (double)n);
-	for (int i = tid; i < TBK_KDE_M; i += nt) {
-		const int r = (int)(__brev((unsigned)i) >> 21);
-		if (i < r) { const double t = sm.x[i].x; sm.x[i].x = sm.x[r].x; sm.x[r].x = t; }
+	// density = irfft(rfft(binned) * FAC): real-input transform through one 1024-point complex FFT each way
+	// (z[j] = g[2j] + i g[2j+1]).  Only the argmax is needed, so positive scale factors are dropped
+	// (binned = g / (delta nobs), the 1/M of the transforms).
+	double2* fa = sm.x;                    // [1024]
+	double2* fb = sm.x + TBK_KDE_M / 2;    // [1024]
+	{
+		double ge[2], go[2];
+		for (int j = 0; j < 2; ++j) { ge[j] = sm.x[2 * (tid + j * nt)].x; go[j] = sm.x[2 * (tid + j * nt) + 1].x; }
+		__syncthreads();
+		for (int j = 0; j < 2; ++j) fa[tid + j * nt] = make_double2(ge[j], go[j]);
+		__syncthreads();
+	}
+	kde_fft1024<false>(fa, fb, P.twiddle);   // Z in fb
+	// X[k] = E[k] + w^k O[k];  Y = X * FAC;  Z'[k] = E'[k] + i O'[k]  (pairs k, N-k handled together, in place)
+	{
+		const double fac1 = 2.0 * (M_PI * bw / range) * (M_PI * bw / range);
+		const int N = TBK_KDE_M / 2;
+		auto fac_of = [&](int J) {
+			const double t = (double)J / (double)TBK_KDE_M * M_PI;
+			return exp(-((double)J * (double)J * fac1)) / (1.0 - 1.0 / 3.0 * (t * t));
+		};
+		for (int k = tid; k <= N / 2; k += nt) {
+			const int kn = (N - k) & (N - 1);
+			const double2 zk = fb[k], zn = fb[kn];
+			// forward post-processing for k and N-k
+			const double2 w = kde_tw<false>(P.twiddle, k), wn = kde_tw<false>(P.twiddle, N - k);
+			const double2 ek = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));      // (Z[k] + conj Z[N-k]) / 2
+			const double2 ok = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));     // (Z[k] - conj Z[N-k]) / (2i)
+			const double2 en = make_double2(ek.x, -ek.y), on = make_double2(ok.x, -ok.y);   // E[N-k] = conj E[k], O likewise
+			double2 xk = cmul(w, ok); xk.x += ek.x; xk.y += ek.y;                           // X[k]
+			double2 xn = cmul(wn, on); xn.x += en.x; xn.y += en.y;                          // X[N-k]
+			const double fk = fac_of(k), fn = fac_of(N - k);
+			const double2 yk = make_double2(xk.x * fk, xk.y * fk), yn = make_double2(xn.x * fn, xn.y * fn);
+			if (k == 0) {
+				// X[0] = Re Z0 + Im Z0, X[N] = Re Z0 - Im Z0 (both real); Z'[0] = (Y0 + YN)/2 + i (Y0 - YN)/2
+				const double y0 = (zk.x + zk.y) * fac_of(0), yN = (zk.x - zk.y) * fac_of(N);
+				fb[0] = make_double2(0.5 * (y0 + yN), 0.5 * (y0 - yN));
+			} else {
+				// inverse pre-processing: E' = (Y[k] + conj Y[N-k]) / 2, O' = (Y[k] - conj Y[N-k]) / 2 * conj(w^k)
+				const double2 e2 = make_double2(0.5 * (yk.x + yn.x), 0.5 * (yk.y - yn.y));
+				const double2 d2 = make_double2(0.5 * (yk.x - yn.x), 0.5 * (yk.y + yn.y));
+				const double2 o2 = cmul(d2, make_double2(w.x, -w.y));
+				fb[k] = make_double2(e2.x - o2.y, e2.y + o2.x);                               // E' + i O'
+				if (kn != k) {
+					const double2 e3 = make_double2(e2.x, -e2.y);                               // E'[N-k] = conj E'[k]
+					const double2 d3 = make_double2(0.5 * (yn.x - yk.x), 0.5 * (yn.y + yk.y));
+					const double2 o3 = cmul(d3, make_double2(wn.x, -wn.y));
+					fb[kn] = make_double2(e3.x - o3.y, e3.y + o3.x);
+				}
+			}
+		}
 	}
 	__syncthreads();
-	for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i].x *= norm;
-	__syncthreads();
-	kde_fft(sm.x, P.twiddle, false);
-	// silverman_transform: FAC_J = exp(-J^2 * 2 (pi bw / RANGE)^2) / (1 - (pi J / M)^2 / 3)
-	const double fac1 = 2.0 * (M_PI * bw / range) * (M_PI * bw / range);
-	for (int i = tid; i < TBK_KDE_M; i += nt) {
-		const int J = (i <= TBK_KDE_M / 2) ? i : TBK_KDE_M - i;
-		const double t = (double)J / (double)TBK_KDE_M * M_PI;
-		const double bc = 1.0 - 1.0 / 3.0 * (t * t);
-		const double fac = exp(-((double)J * (double)J * fac1)) / bc;
-		sm.x[i].x *= fac; sm.x[i].y *= fac;
-	}
-	__syncthreads();
-	// inverse: bit-reverse then DIT with conjugate twiddles
-	for (int i = tid; i < TBK_KDE_M; i += nt) {
-		const int r = (int)(__brev((unsigned)i) >> 21);
-		if (i < r) { const double2 t = sm.x[i]; sm.x[i] = sm.x[r]; sm.x[r] = t; }
-	}
-	__syncthreads();
-	kde_fft(sm.x, P.twiddle, true);
+	kde_fft1024<true>(fb, fa, P.twiddle);    // z' in fa: density[2j] = Re, density[2j+1] = Im
 	// argmax (first maximum) of the density
 	double bv = -INFINITY; int bi = 0x7fffffff;
-	for (int i = tid; i < TBK_KDE_M; i += nt) {
-		const double d = sm.x[i].x;
-		if (d > bv) { bv = d; bi = i; }
+	for (int j = tid; j < TBK_KDE_M / 2; j += nt) {
+		const double2 d = fa[j];
+		if (d.x > bv) { bv = d.x; bi = 2 * j; }
+		if (d.y > bv) { bv = d.y; bi = 2 * j + 1; }
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
