@@ -254,3 +254,64 @@ def test_full_size_properties(full_stack):
 	assert torch.equal(m2[0], mask[2]) and torch.allclose(b2[0], bkg[2], rtol=1e-6, atol=0)
 	# the background is smooth at mesh scale: bounded by the unmasked data range, no NaN leakage
 	assert float(bkg.min()) > 0 and float(bkg.max()) < 8e4
+
+
+# ---- independent implementations agree --------------------------------------------------------
+def test_kernel_variants_agree(monkeypatch):
+	"""
+	TBK_TILE_KERNEL selects independent implementations of the mesh statistics / zeropoint / ring gather
+	(0: generic CTA-per-mesh kernels with iterated histogram selection and full passes, 1: one warp per mesh,
+	2: block-cooperative bucketed kernels).  They must give the same statistics bit for bit in the median and
+	to rounding in mean / std, and the same backgrounds.
+	"""
+	case = CASES['tess_small']()
+	imgs = case['images']
+	H, W = imgs.shape[1:]
+	cube = torch.from_numpy(imgs).cuda()
+	meta = pb.meta_from_headers(case['headers'])
+	res = {}
+	for variant in ('0', '1', '2'):
+		monkeypatch.setenv('TBK_TILE_KERNEL', variant)
+		fit = pb.BackgroundFitter((H, W), True, case['camera'], case['ccd'], xycen=case['xycen'], **case['fit_kwargs'])
+		bkg, mask, st = fit.fit(cube, meta)
+		ws = fit.debug_workspace()
+		res[variant] = (bkg.cpu().numpy(), mask.cpu().numpy(), ws['tile_base'].copy(), ws['tile_nf'].copy(), fit.status_to_numpy(st).copy())
+	ref = res['0']
+	for variant in ('1', '2'):
+		got = res[variant]
+		assert np.array_equal(got[1], ref[1])
+		for idx, (a, b) in enumerate(((got[2], ref[2]), (got[3], ref[3]))):
+			assert np.array_equal(a['nfin'], b['nfin'])
+			ok = b['nfin'] > 0
+			if idx == 0:
+				# raw float32 pixels: the medians are exact order statistics of identical inputs
+				assert np.array_equal(a['med'][ok], b['med'][ok])
+			else:
+				# residuals x - radial: the zeropoint (hence radial) differs at rounding level between variants
+				np.testing.assert_allclose(a['med'][ok], b['med'][ok], rtol=1e-11, atol=1e-11)
+			np.testing.assert_allclose(a['mean'][ok], b['mean'][ok], rtol=1e-11, atol=1e-11)
+			np.testing.assert_allclose(a['std'][ok], b['std'][ok], rtol=1e-9)
+		np.testing.assert_allclose(got[4]['zeropoint'], ref[4]['zeropoint'], rtol=1e-12)
+		assert in_tolerance(got[0], ref[0]).all()
+		np.testing.assert_allclose(got[0], ref[0], rtol=1e-6)
+
+
+def test_fit_stack_streams_match_single_launch():
+	"""Chunked multi-stream driver == one launch over the whole stack."""
+	case = CASES['prepare']()
+	imgs = case['images']
+	n, H, W = imgs.shape
+	fit = pb.BackgroundFitter((H, W), True, case['camera'], case['ccd'], xycen=case['xycen'], **case['fit_kwargs'])
+	cube = torch.from_numpy(imgs).cuda()
+	meta = pb.meta_from_headers(case['headers'])
+	b0, m0, _ = fit.fit(cube, meta)
+	b1 = torch.empty_like(cube); m1 = torch.empty(cube.shape, dtype=torch.uint8, device='cuda')
+	fit.fit_stack(cube, meta, b1, m1, chunk=2, nstreams=3)
+	torch.cuda.synchronize()
+	assert torch.equal(m0, m1)
+	assert torch.allclose(b0, b1, rtol=1e-6, atol=0)
+	# and through host buffers (the end-to-end path)
+	hb = torch.empty((n, H, W), dtype=torch.float32).pin_memory(); hm = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
+	pb.fit_stack_host(fit, torch.from_numpy(imgs).pin_memory(), meta, hb, hm, chunk=4)
+	torch.cuda.synchronize()
+	assert torch.equal(hm, m0.cpu()) and torch.allclose(hb, b0.cpu(), rtol=1e-6, atol=0)
