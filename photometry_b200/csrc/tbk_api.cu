@@ -31,7 +31,7 @@ struct tbk_plan {
 	std::vector<void*> allocs;
 	int* zero_flags;
 	int zero_cap;
-	int tile_kernel;   // TBK_TILE_KERNEL: 0 = generic CTA-per-mesh kernels, 1 = one warp per mesh, 2 = two warps per mesh (default)
+	int tile_kernel;   // TBK_TILE_KERNEL: 0 = generic CTA-per-mesh kernels, 1 = one warp per mesh (registers), 2 = two warps per mesh (registers), 3 = two warps per mesh, keys staged in shared memory (default)
 	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow;
 };
 
@@ -137,7 +137,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
 	p->zero_flags = nullptr; p->zero_cap = 0;
-	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 2; if (p->tile_kernel < 0 || p->tile_kernel > 2) p->tile_kernel = 2; }
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel < 0 || p->tile_kernel > 3) p->tile_kernel = 3; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;

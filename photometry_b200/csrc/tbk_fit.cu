@@ -281,6 +281,82 @@ __global__ void __launch_bounds__(64, TW2_MINB) k_tile_base_w2(PlanDev P, Worksp
 	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
 
+// K_tile_base_w3: as k_tile_base_w2, but the validated keys are staged in shared memory and the per-pixel
+// loops are rolled (small code: the unrolled register version is bound by instruction fetch).
+// Thread t, load i (0..15) owns row 4i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3.
+template <bool HAS_EXTRA>
+__global__ void __launch_bounds__(64, 10) k_tile_base_w3(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
+{
+	__shared__ TwBlockSmem<TwF32, 2> sm;
+	__shared__ uint32_t s_sb[64];
+	__shared__ int s_nbad, s_nz;
+	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	FfiCtl& c = ws.ctl[b];
+	const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
+	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + lrow0) * P.W + tx * TBK_TILE + lcol;
+	const size_t step = (size_t)4 * P.W;
+	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
+	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
+	s_sb[tid] = TW_INVALID;
+	if (tid == 0) { s_nbad = 0; s_nz = 0; }
+	__syncthreads();
+	uint32_t nz = 0u;
+	int nbad = 0;
+#pragma unroll 1
+	for (int a = 0; a < 8; ++a) {   // rows 8a .. 8a+7 of the mesh: loads 2a and 2a+1 of both warps
+		float4 r[2];
+#pragma unroll
+		for (int h = 0; h < 2; ++h) r[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(2 * a + h) * step));
+		uint32_t smin = TW_INVALID;
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const size_t off = base + (size_t)(2 * a + h) * step;
+			uint32_t ex = 0u;
+			if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
+			const float x4[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
+			uint32_t kk[4], m = 0u;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t k = __float_as_uint(x4[q] + 0.0f);   // -0.0 -> +0.0
+				nz |= k;
+				bool ok = (k <= cut) && !excl;
+				if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
+				m |= ok ? 0u : (1u << (8 * q));
+				kk[q] = ok ? k : TW_INVALID;
+				smin = min(smin, kk[q]);
+			}
+			nbad += __popc(m);
+			*reinterpret_cast<unsigned int*>(mask_out + off) = m;
+			*reinterpret_cast<uint4*>(&sm.tw.keys[(lrow0 + 4 * (2 * a + h)) * TBK_TILE + lcol]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+		}
+		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 1));
+		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 16));
+		if ((lane & 17) == 0) atomicMin(&s_sb[a * 8 + (lane >> 1)], smin);
+	}
+	nbad = __reduce_add_sync(0xffffffffu, nbad);
+	nz = __reduce_or_sync(0xffffffffu, nz);
+	if (lane == 0) { atomicAdd(&s_nbad, nbad); if (nz) atomicOr(&s_nz, 1); }
+	__syncthreads();
+	const uint32_t mysb = s_sb[tid];
+	ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + tid] = __uint_as_float(mysb);
+	const int n = 4096 - s_nbad;
+	if (tid == 0) {
+		if (s_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+		if (n > 0) atomicAdd(&c.n_valid, n);
+	}
+	if (w == 0) {
+		uint32_t kmin = min(mysb, s_sb[tid + 32]);
+		kmin = __reduce_min_sync(0xffffffffu, kmin);
+		if (lane == 0 && kmin != TW_INVALID) atomicMin(&c.min_bits, kmin);
+	}
+	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
+	TileStat st; bool writer;
+	tile_block_stats_staged<TwF32, 2>(sm, n, st, writer);
+	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+}
+
 // K_post_base: all-zero rule (pixel_flags.py:54-56), all-masked early-out (backgrounds.py:101-102),
 // zeropoint of round 1 (backgrounds.py:171).
 __global__ void k_post_base(PlanDev P, Workspace ws, tbk_ffi_status* status, int B)
@@ -568,7 +644,9 @@ __global__ void __launch_bounds__(256) k_ring_gather_t(PlanDev P, Workspace ws, 
 // ---------------------------------------------------------------------------------------------
 // K_ring_kde: mode of a Gaussian FFT-KDE per ring (backgrounds.py:21-33 + statsmodels 0.13.2
 // KDEUnivariate.fit(gridsize=2000); see oracle/backgrounds_oracle.py:kde_density).
+#ifndef TBK_KDE_NT
 #define TBK_KDE_NT 512
+#endif
 #define TBK_KDE_CAND 256
 struct KdeSmem {
 	double2 x[TBK_KDE_M];
@@ -681,7 +759,7 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 			__syncthreads();
 			// exclusive scan (thread t owns bins 2t, 2t+1 for 512 threads)
 			const int per = TBK_NBINS / TBK_KDE_NT;
-			unsigned loc[2], tsum = 0;
+			unsigned loc[TBK_NBINS / TBK_KDE_NT], tsum = 0;
 			for (int j = 0; j < per; ++j) { loc[j] = sm.sel.hist[tid * per + j]; tsum += loc[j]; }
 			unsigned inc = tsum;
 			for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += u; }
@@ -803,10 +881,11 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 	double2* fa = sm.x;                    // [1024]
 	double2* fb = sm.x + TBK_KDE_M / 2;    // [1024]
 	{
-		double ge[2], go[2];
-		for (int j = 0; j < 2; ++j) { ge[j] = sm.x[2 * (tid + j * nt)].x; go[j] = sm.x[2 * (tid + j * nt) + 1].x; }
+		constexpr int RP = TBK_KDE_M / 2 / TBK_KDE_NT;
+		double ge[RP], go[RP];
+		for (int j = 0; j < RP; ++j) { ge[j] = sm.x[2 * (tid + j * nt)].x; go[j] = sm.x[2 * (tid + j * nt) + 1].x; }
 		__syncthreads();
-		for (int j = 0; j < 2; ++j) fa[tid + j * nt] = make_double2(ge[j], go[j]);
+		for (int j = 0; j < RP; ++j) fa[tid + j * nt] = make_double2(ge[j], go[j]);
 		__syncthreads();
 	}
 	kde_fft1024<false>(fa, fb, P.twiddle);   // Z in fb
@@ -1039,7 +1118,7 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
 // K_tile_round_w: same result as k_tile_round with the bucketed algorithm of tbk_tile_warp.cuh on float64
 // residuals.  128 threads per mesh; thread t, load i (0..7) owns row 8i + 2(t/32) + (t%32)/16, columns 4(t%16)..+3.
 #ifndef TWR_MINB
-#define TWR_MINB 4
+#define TWR_MINB 5
 #endif
 __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
@@ -1054,11 +1133,14 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 	const int tile = P.nonflat_tiles[slot];
 	const int ty = tile / P.nx, tx = tile % P.nx;
 	const int lane = tid & 31, w = tid >> 5;
-	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
-	unsigned long long key[32];
-#pragma unroll
-	for (int i = 0; i < 8; ++i) {
-		const int gy = ty * TBK_TILE + 8 * i + 2 * w + (lane >> 4);
+	const int lcol = (lane & 15) << 2, gx = tx * TBK_TILE + lcol;
+	__shared__ int s_n;
+	if (tid == 0) s_n = 0;
+	__syncthreads();
+	int n = 0;
+#pragma unroll 1
+	for (int i = 0; i < 8; ++i) {   // rolled: the radial evaluation is ~150 instructions per pixel
+		const int lrow = 8 * i + 2 * w + (lane >> 4), gy = ty * TBK_TILE + lrow;
 		const size_t off = (size_t)b * P.H * P.W + (size_t)gy * P.W + gx;
 		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
 		const unsigned int m = __ldg(reinterpret_cast<const unsigned int*>(mask + off));
@@ -1066,12 +1148,15 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			unsigned long long k = ~0ULL;
-			if (!((m >> (8 * q)) & 0xFFu)) k = dkey((double)x4[q] - radial_value_s(rs, pixel_radius(P, gy, gx + q)));
-			key[4 * i + q] = k;
+			if (!((m >> (8 * q)) & 0xFFu)) { k = dkey((double)x4[q] - radial_value_s(rs, pixel_radius(P, gy, gx + q))); ++n; }
+			sm.tw.keys[lrow * TBK_TILE + lcol + q] = k;
 		}
 	}
+	n = __reduce_add_sync(0xffffffffu, n);
+	if (lane == 0) atomicAdd(&s_n, n);
+	__syncthreads();
 	TileStat st; bool writer;
-	tile_block_stats<TwF64, 4, 32>(key, sm, st, writer);
+	tile_block_stats_staged<TwF64, 4>(sm, s_n, st, writer);
 	if (writer) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
 }
 
@@ -1351,6 +1436,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	const int gb = (B + 127) / 128;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
 	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 3 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (tile_kernel == 2 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (tile_kernel == 2) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<true><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));

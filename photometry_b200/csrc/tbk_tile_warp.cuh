@@ -562,3 +562,109 @@ __device__ void tile_block_stats(const typename T::K (&key)[VPT], TwBlockSmem<T,
 	for (int q = 0; q < NW; ++q) { s1c += sm.red[0][q][0]; s2c += sm.red[0][q][1]; t1 += sm.red[1][q][0]; t2 += sm.red[1][q][1]; tn += sm.ntl[q]; }
 	out = tw_iterate<T>(sm.tw.keys, sm.tw.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Staged variant: the (validated) keys of the mesh sit in sm.tw.keys in any order when this is called
+// (INVALID entries allowed), nvalid is known.  Compared with tile_block_stats the per-element passes are
+// rolled loops over shared memory -- the fully unrolled register version is ~115 KB of SASS and stalls on
+// instruction fetch -- and only the in-place scatter holds the keys in registers.
+template <typename T, int NW>
+__device__ void tile_block_stats_staged(TwBlockSmem<T, NW>& sm, int nvalid, TileStat& out, bool& writer)
+{
+	typedef typename T::K K;
+	constexpr int NT = 32 * NW, VPT = TBK_NPIX_TILE / NT;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const K INV = T::invalid();
+	writer = (tid == 0);
+	out.mean = out.med = out.std = nan_d();
+	out.nfin = 0; out.pad = 0;
+	if (nvalid == 0) return;
+	for (int i = tid; i < TW_CNT_WORDS; i += NT) sm.tw.cnt[i] = 0u;
+	if (tid == 0) sm.constant = 0;
+	// ---- robust window from 2 x 32 samples spread over the mesh (warp 0)
+	if (w == 0) {
+		double med = 0.0, iqr = 0.0; int sets = 0;
+#pragma unroll
+		for (int t = 0; t < 2; ++t) {
+			const K k = warp_bitonic32<K>(sm.tw.keys[(lane * 131 + 17 + t * 2053) & (TBK_NPIX_TILE - 1)], lane);
+			const int m = __popc(__ballot_sync(0xffffffffu, k != INV));
+			if (m >= 8) {
+				med += T::val(__shfl_sync(0xffffffffu, k, m >> 1));
+				iqr += T::val(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - T::val(__shfl_sync(0xffffffffu, k, m >> 2));
+				++sets;
+			}
+		}
+		double w0, w1, pv;
+		if (sets && iqr > 0.0) {
+			med /= (double)sets;
+			const double half = 10.0 * (iqr / (double)sets) / 1.349;
+			w0 = med - half; w1 = med + half; pv = T::pivot_of(med);
+		} else {
+			// degenerate sample: full data range (constant meshes end here)
+			K kmin = T::padkey(), kmax = 0;
+			for (int i = lane; i < TBK_NPIX_TILE; i += 32) { const K k = sm.tw.keys[i]; if (k != INV) { kmin = min(kmin, k); kmax = max(kmax, k); } }
+			for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
+			w0 = T::val(kmin); w1 = T::val(kmax); pv = w0;
+			if (lane == 0) { sm.kmin = kmin; if (!(w1 > w0)) sm.constant = 1; }
+		}
+		if (lane == 0) { sm.bm = T::make_map(w0, w1); sm.pivot = pv; }
+	}
+	__syncthreads();
+	if (sm.constant) {  // all values equal: sigma = 0, nothing is clipped
+		out.mean = out.med = T::val(sm.kmin); out.std = 0.0; out.nfin = nvalid;
+		return;
+	}
+	const typename T::Map bm = sm.bm;
+	const double pivot = sm.pivot;
+	// ---- pass 1: counts (rolled)
+#pragma unroll 4
+	for (int j = 0; j < VPT; ++j) {
+		const K k = sm.tw.keys[tid + NT * j];
+		const int b = T::bin(bm, k);
+		if (k != INV) atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4));
+	}
+	// ---- the keys move to registers for the in-place scatter
+	K key[VPT];
+#pragma unroll
+	for (int j = 0; j < VPT; ++j) key[j] = sm.tw.keys[tid + NT * j];
+	__syncthreads();
+	if (w == 0) tw_scan_counts(sm.tw.cnt, lane);
+	__syncthreads();
+	// ---- pass 2: scatter in groups of 8
+#pragma unroll
+	for (int g = 0; g < VPT / 8; ++g) {
+		uint32_t old[8]; int sh[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const K k = key[8 * g + j];
+			const int b = T::bin(bm, k);
+			sh[j] = (b & 1) << 4;
+			old[j] = 0u;
+			if (k != INV) old[j] = atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << sh[j]);
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const K k = key[8 * g + j];
+			if (k != INV) sm.tw.keys[(old[j] >> sh[j]) & 0xFFFFu] = k;
+		}
+	}
+	__syncthreads();
+	// ---- moments: all warps sweep the bucketed keys
+	const uint32_t t0e = tw_cend(sm.tw.cnt, 0), t1s = tw_cstart(sm.tw.cnt, TW_NB - 1);
+	double c1 = 0.0, c2 = 0.0, q1 = 0.0, q2 = 0.0; int tn = 0;
+	for (uint32_t p = tid; p < (uint32_t)nvalid; p += NT) {
+		const double d = T::val(sm.tw.keys[p]) - pivot;
+		if (p >= t0e && p < t1s) { c1 += d; c2 = fma(d, d, c2); }
+		else { ++tn; q1 += d; q2 = fma(d, d, q2); }
+	}
+	c1 = warp_sum_d(c1); c2 = warp_sum_d(c2);
+	tn = __reduce_add_sync(0xffffffffu, tn);
+	if (__any_sync(0xffffffffu, tn != 0)) { q1 = warp_sum_d(q1); q2 = warp_sum_d(q2); }
+	if (lane == 0) { sm.red[0][w][0] = c1; sm.red[0][w][1] = c2; sm.red[1][w][0] = q1; sm.red[1][w][1] = q2; sm.ntl[w] = tn; }
+	__syncthreads();
+	if (w != 0) { writer = false; return; }
+	double s1c = 0.0, s2c = 0.0, t1 = 0.0, t2 = 0.0; tn = 0;
+#pragma unroll
+	for (int q = 0; q < NW; ++q) { s1c += sm.red[0][q][0]; s2c += sm.red[0][q][1]; t1 += sm.red[1][q][0]; t2 += sm.red[1][q][1]; tn += sm.ntl[q]; }
+	out = tw_iterate<T>(sm.tw.keys, sm.tw.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
+}
