@@ -711,8 +711,17 @@ __global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws
 	const double* __restrict__ v = ws.ring_v + (size_t)b * P.nringpix;
 	double* out = ws.s2_raw + (size_t)b * P.nrings + ring;
 
+	// sweep over the ring's samples: four independent loads in flight per thread (the array lives in L2)
 	auto each = [&](auto f) {
-		for (int i = lo + tid; i < hi; i += nt) { const double d = v[i]; if (d == d) f(d); }
+		int i = lo + tid;
+		for (; i + 3 * nt < hi; i += 4 * nt) {
+			const double d0 = v[i], d1 = v[i + nt], d2 = v[i + 2 * nt], d3 = v[i + 3 * nt];
+			if (d0 == d0) f(d0);
+			if (d1 == d1) f(d1);
+			if (d2 == d2) f(d2);
+			if (d3 == d3) f(d3);
+		}
+		for (; i < hi; i += nt) { const double d = v[i]; if (d == d) f(d); }
 	};
 
 	int n = 0; double mn = INFINITY, mx = -INFINITY, s1 = 0.0, dmy = 0.0;
