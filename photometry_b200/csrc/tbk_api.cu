@@ -137,7 +137,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
 	p->zero_flags = nullptr; p->zero_cap = 0;
-	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel < 0 || p->tile_kernel > 3) p->tile_kernel = 3; }
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel < 0 || p->tile_kernel > 4) p->tile_kernel = 3; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;

@@ -284,11 +284,12 @@ __global__ void __launch_bounds__(64, TW2_MINB) k_tile_base_w2(PlanDev P, Worksp
 // K_tile_base_w3: as k_tile_base_w2, but the validated keys are staged in shared memory and the per-pixel
 // loops are rolled (small code: the unrolled register version is bound by instruction fetch).
 // Thread t, load i (0..15) owns row 4i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3.
-template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(64, 10) k_tile_base_w3(PlanDev P, Workspace ws,
+template <bool HAS_EXTRA, int NW>
+__global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
 {
-	__shared__ TwBlockSmem<TwF32, 2> sm;
+	__shared__ TwBlockSmem<TwF32, NW> sm;
+	constexpr int LPA = 4 / NW;   // loads per 8-row band: a load step covers 2 NW rows
 	__shared__ uint32_t s_sb[64];
 	__shared__ int s_nbad, s_nz;
 	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -296,23 +297,23 @@ __global__ void __launch_bounds__(64, 10) k_tile_base_w3(PlanDev P, Workspace ws
 	FfiCtl& c = ws.ctl[b];
 	const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
 	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + lrow0) * P.W + tx * TBK_TILE + lcol;
-	const size_t step = (size_t)4 * P.W;
+	const size_t step = (size_t)(2 * NW) * P.W;
 	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
 	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
-	s_sb[tid] = TW_INVALID;
+	if (tid < 64) s_sb[tid] = TW_INVALID;
 	if (tid == 0) { s_nbad = 0; s_nz = 0; }
 	__syncthreads();
 	uint32_t nz = 0u;
 	int nbad = 0;
 #pragma unroll 1
 	for (int a = 0; a < 8; ++a) {   // rows 8a .. 8a+7 of the mesh: loads 2a and 2a+1 of both warps
-		float4 r[2];
+		float4 r[LPA];
 #pragma unroll
-		for (int h = 0; h < 2; ++h) r[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(2 * a + h) * step));
+		for (int h = 0; h < LPA; ++h) r[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(LPA * a + h) * step));
 		uint32_t smin = TW_INVALID;
 #pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			const size_t off = base + (size_t)(2 * a + h) * step;
+		for (int h = 0; h < LPA; ++h) {
+			const size_t off = base + (size_t)(LPA * a + h) * step;
 			uint32_t ex = 0u;
 			if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
 			const float x4[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(64, 10) k_tile_base_w3(PlanDev P, Workspace ws
 			}
 			nbad += __popc(m);
 			*reinterpret_cast<unsigned int*>(mask_out + off) = m;
-			*reinterpret_cast<uint4*>(&sm.tw.keys[(lrow0 + 4 * (2 * a + h)) * TBK_TILE + lcol]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+			*reinterpret_cast<uint4*>(&sm.tw.keys[(lrow0 + 2 * NW * (LPA * a + h)) * TBK_TILE + lcol]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
 		}
 		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 1));
 		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 16));
@@ -339,21 +340,21 @@ __global__ void __launch_bounds__(64, 10) k_tile_base_w3(PlanDev P, Workspace ws
 	nz = __reduce_or_sync(0xffffffffu, nz);
 	if (lane == 0) { atomicAdd(&s_nbad, nbad); if (nz) atomicOr(&s_nz, 1); }
 	__syncthreads();
-	const uint32_t mysb = s_sb[tid];
-	ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + tid] = __uint_as_float(mysb);
+	const uint32_t mysb = s_sb[tid & 63];
+	if (tid < 64) ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + tid] = __uint_as_float(mysb);
 	const int n = 4096 - s_nbad;
 	if (tid == 0) {
 		if (s_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
 		if (n > 0) atomicAdd(&c.n_valid, n);
 	}
 	if (w == 0) {
-		uint32_t kmin = min(mysb, s_sb[tid + 32]);
+		uint32_t kmin = min(s_sb[lane], s_sb[lane + 32]);
 		kmin = __reduce_min_sync(0xffffffffu, kmin);
 		if (lane == 0 && kmin != TW_INVALID) atomicMin(&c.min_bits, kmin);
 	}
 	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
 	TileStat st; bool writer;
-	tile_block_stats_staged<TwF32, 2>(sm, n, st, writer);
+	tile_block_stats_staged<TwF32, NW>(sm, n, st, writer);
 	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
 
@@ -1445,8 +1446,10 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	const int gb = (B + 127) / 128;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
 	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 3 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 4 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 4><<<gt, 128, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 4) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 4><<<gt, 128, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 3 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (tile_kernel == 2 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (tile_kernel == 2) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<true><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
