@@ -234,9 +234,19 @@ def run_b200(args):
 	launches_per_call = {'tile_base': 1, 'tile_round': 3, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
 	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
 	peak, peak_src = load_peaks()
+	# DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture
+	traffic = None
+	try:
+		with open(os.path.join(ROOT, 'profiles', 'r01_ncu_fit_summary.json')) as fid:
+			prof_json = json.load(fid)
+		for kname, e in prof_json['kernels'].items():
+			if kname.split('<')[0] in ('k_' + dom, 'k_' + dom + '_w', 'k_' + dom + '_w3', 'k_' + dom + '_t'):
+				traffic = (e['dram_read_bytes'] + e['dram_write_bytes']) / e['launches'] / prof_json['ffis_per_launch'] * min(chunk, n)
+	except (OSError, KeyError, ValueError):
+		traffic = None
 	achieved = ALGO_BYTES_PER_FFI * min(chunk, n) / (dom_launch_ms * 1e-3) / 1e9
 	roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-		"traffic": None, "peak_source": peak_src, "launch_ms": dom_launch_ms, "ffis_per_launch": min(chunk, n),
+		"traffic": traffic, "traffic_source": "profiles/r01_ncu_fit_summary.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, scaled to this launch size)", "peak_source": peak_src, "launch_ms": dom_launch_ms, "ffis_per_launch": min(chunk, n),
 		"whole_path_achieved": value / world * ALGO_BYTES_PER_FFI / 1e9, "whole_path_frac": value / world * ALGO_BYTES_PER_FFI / 1e9 / peak}
 
 	# ---- end to end: pinned host stack -> device -> fit -> pinned host results (same metric)
