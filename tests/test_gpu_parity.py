@@ -315,3 +315,80 @@ def test_fit_stack_streams_match_single_launch():
 	pb.fit_stack_host(fit, torch.from_numpy(imgs).pin_memory(), meta, hb, hm, chunk=4)
 	torch.cuda.synchronize()
 	assert torch.equal(hm, m0.cpu()) and torch.allclose(hb, b0.cpu(), rtol=1e-6, atol=0)
+
+
+# ---- edge cases: shapes, degenerate rings, ties, heavy masking -----------------------------------
+def _compare_with_oracle(img, hdr=None, xycen=None, extra=None, **kw):
+	tess = hdr is not None
+	H, W = img.shape
+	fit = pb.BackgroundFitter((H, W), tess, hdr['CAMERA'] if tess else 0, hdr['CCD'] if tess else 0, xycen=xycen, **kw)
+	cube = torch.from_numpy(img[None].copy()).cuda()
+	ex = torch.from_numpy(extra[None].copy()).cuda() if extra is not None else None
+	bkg, mask, st = fit.fit(cube, pb.meta_from_headers([hdr]) if tess else None, ex)
+	torch.cuda.synchronize()
+	st = fit.status_to_numpy(st)[0]
+	d = {}
+	if tess:
+		rb, rm = oracle.fit_background(oracle.FFIImageLite(img, hdr, True), xycen=xycen, extra_mask=extra, diagnostics=d, **kw)
+	else:
+		rb, rm = oracle.fit_background(img, extra_mask=extra, diagnostics=d, **kw)
+	assert np.array_equal(mask[0].cpu().numpy().astype(bool), rm)
+	ok = in_tolerance(bkg[0].cpu().numpy(), rb)
+	assert ok.all(), f"{(~ok).sum()} pixels outside tolerance"
+	return st, d
+
+
+@pytest.mark.parametrize('shape', [(64, 64), (64, 192), (192, 128)])
+def test_small_and_non_square_shapes(shape):
+	rng = np.random.default_rng(shape[0] + shape[1])
+	img = (120 + 0.05 * np.arange(shape[1])[None, :] + 6 * rng.standard_normal(shape)).astype('float32')
+	img[10:14, 20:26] += 3000
+	_compare_with_oracle(img)
+
+
+def test_quantised_pixels_with_many_ties():
+	"""Integer-valued pixels: hundreds of equal values per mesh exercise the large-bin exact selection."""
+	rng = np.random.default_rng(8)
+	img = np.round(100 + 3 * rng.standard_normal((256, 256))).astype('float32')
+	img[:64, :64] = 77.0                   # a constant mesh
+	img[64:128, :64] = np.round(50 + 0.4 * rng.standard_normal((64, 64)))  # only 3-4 distinct values
+	img[200:230, 100:140] += 800
+	_compare_with_oracle(img)
+	hdr = header(1, 2, 0)
+	_compare_with_oracle(img, hdr, xycen=(-20.0, 300.0), radial_cutoff=230, radial_pixel_step=15)
+
+
+def test_heavily_contaminated_meshes():
+	"""Meshes where 45 % of the pixels are bright: clipping runs all five iterations on a bimodal mesh."""
+	rng = np.random.default_rng(9)
+	img = (300 + 10 * rng.standard_normal((256, 256))).astype('float32')
+	sel = rng.uniform(size=(256, 256)) < 0.45
+	img[sel] += rng.uniform(50, 4000, sel.sum()).astype('float32')
+	_compare_with_oracle(img)
+
+
+def test_radial_profile_degenerate_cases():
+	"""Too few finite rings -> no radial component (backgrounds.py:192-197); rings with 0 / 1 samples -> NaN."""
+	rng = np.random.default_rng(10)
+	H, W = 192, 192
+	img = (150 + 5 * rng.standard_normal((H, W))).astype('float32')
+	hdr = header(2, 3, 0)
+	# (a) only three rings exist: the spline needs four points ("m must be > k") -> radial = 0 every round
+	st, d = _compare_with_oracle(img, hdr, xycen=(-10.0, 230.0), radial_cutoff=295, radial_pixel_step=15)
+	assert (st['radial_ok'][:3] == 0).all() and not any(r['radial_ok'] for r in d['rounds'])
+	# (b) several rings masked out entirely by the extra mask, one ring left with a single pixel
+	xycen = (-10.0, 230.0)
+	r, bins, cen = oracle.radial_geometry((H, W), xycen, 200, 10)
+	extra = (r >= bins[3]) & (r < bins[6])
+	ring7 = np.argwhere((r >= bins[7]) & (r < bins[8]))
+	extra[(r >= bins[7]) & (r < bins[8])] = True
+	extra[ring7[0][0], ring7[0][1]] = False
+	st, d = _compare_with_oracle(img, hdr, xycen=xycen, extra=extra, radial_cutoff=200, radial_pixel_step=10)
+	assert st['radial_ok'][0] == 1 and np.isnan(d['rounds'][0]['s2_raw'][7]) and np.isnan(d['rounds'][0]['s2_raw'][4])
+
+
+@pytest.mark.parametrize('kw', [dict(bkgiters=5), dict(radial_smooth=7, radial_pixel_step=8), dict(flux_cutoff=250.0)])
+def test_more_parameter_variants(kw):
+	case = CASES['tess_small']()
+	kw2 = dict(case['fit_kwargs']); kw2.update(kw)
+	_compare_with_oracle(case['images'][1], case['headers'][1], xycen=case['xycen'], **kw2)
