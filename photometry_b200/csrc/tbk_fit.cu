@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(256) k_ring_gather_t(PlanDev P, Workspace ws, 
 // K_ring_kde: mode of a Gaussian FFT-KDE per ring (backgrounds.py:21-33 + statsmodels 0.13.2
 // KDEUnivariate.fit(gridsize=2000); see oracle/backgrounds_oracle.py:kde_density).
 #ifndef TBK_KDE_NT
-#define TBK_KDE_NT 512
+#define TBK_KDE_NT 256   // 4 CTAs per SM (64 registers, 49 KB shared memory each)
 #endif
 #define TBK_KDE_CAND 256
 struct KdeSmem {
@@ -678,11 +678,10 @@ __device__ __forceinline__ double2 kde_tw(const double2* __restrict__ tw, int q)
 template <bool INV>
 __device__ __forceinline__ void kde_fft1024(double2* a, double2* b, const double2* __restrict__ tw)
 {
-	const int i = threadIdx.x;
 	double2* x = a; double2* y = b;
 #pragma unroll
 	for (int p = 1; p < 1024; p <<= 2) {
-		if (i < 256) {
+		for (int i = threadIdx.x; i < 256; i += blockDim.x) {
 			const int k = i & (p - 1), j = ((i - k) << 2) + k, q = k * (512 / p);
 			const double2 u0 = x[i];
 			const double2 u1 = cmul(x[i + 256], kde_tw<INV>(tw, q));
@@ -701,7 +700,7 @@ __device__ __forceinline__ void kde_fft1024(double2* a, double2* b, const double
 	}
 }
 
-__global__ void __launch_bounds__(TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws)
+__global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(PlanDev P, Workspace ws)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	KdeSmem& sm = *reinterpret_cast<KdeSmem*>(smraw);
