@@ -983,103 +983,127 @@ __device__ double nanmedian_small(const double* x, int lo, int hi)
 }
 
 struct RadialSmem {
-	double ky[TBK_MAX_RINGS], h[TBK_MAX_RINGS], dl[TBK_MAX_RINGS], dg[TBK_MAX_RINGS], du[TBK_MAX_RINGS],
-		rhs[TBK_MAX_RINGS], M2[TBK_MAX_RINGS];
+	double raw[TBK_MAX_RINGS], s2[TBK_MAX_RINGS], kx[TBK_MAX_RINGS], ky[TBK_MAX_RINGS], h[TBK_MAX_RINGS], dl[TBK_MAX_RINGS],
+		dg[TBK_MAX_RINGS], du[TBK_MAX_RINGS], rhs[TBK_MAX_RINGS], M2[TBK_MAX_RINGS];
+	int m;
 };
 
-// one CTA per FFI; the profile has <= TBK_MAX_RINGS points, so a single thread does the serial work
-__global__ void k_radial_fit(PlanDev P, Workspace ws, tbk_ffi_status* status, int round, int B)
+// one warp per FFI: the window medians, right-hand sides, piece coefficients and lookup tables are spread over
+// the lanes; only the knot compaction and the tridiagonal solve (<= TBK_MAX_RINGS unknowns) are serial.
+__global__ void __launch_bounds__(32) k_radial_fit(PlanDev P, Workspace ws, tbk_ffi_status* status, int round, int B)
 {
 	__shared__ RadialSmem rsm;
-	const int b = blockIdx.x;
-	if (b >= B || threadIdx.x != 0) return;
+	const int b = blockIdx.x, lane = threadIdx.x;
+	if (b >= B) return;
 	FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
 	const int n = P.nrings;
-	const double* raw = ws.s2_raw + (size_t)b * n;
-	double* s2 = ws.s2_hist + ((size_t)b * P.bkgiters + round) * n;
+	const double* raw_g = ws.s2_raw + (size_t)b * n;
+	double* s2g = ws.s2_hist + ((size_t)b * P.bkgiters + round) * n;
+	for (int i = lane; i < n; i += 32) rsm.raw[i] = raw_g[i];
+	__syncwarp();
+	const double* raw = rsm.raw;
 	const int w = P.radial_smooth;
 	if (w > 0) {
-		// bottleneck.move_median(min_count=1) rolled by -w//2+1, then the edge fix-up loop
-		const int k = -(((-w) >> 1) + 1);  // python: -( (-w)//2 + 1 )
-		for (int i = 0; i < n; ++i) {
-			const int src = (i + k) % n;  // np.roll
-			s2[i] = nanmedian_small(raw, max(0, src - w + 1), src + 1);
-		}
-		for (int e = 0; e < w / 2 + 1; ++e) {
-			s2[e] = nanmedian_small(raw, 0, min(n, e + 2));
-			s2[n - 1 - e] = nanmedian_small(raw, max(0, n - (e + 2)), n);
+		const int ne = w / 2 + 1;                 // points fixed up at each end
+		const int k = -(((-w) >> 1) + 1);         // python: -( (-w)//2 + 1 ), the np.roll shift
+		if (n >= 2 * ne) {
+			// bottleneck.move_median(min_count=1) rolled by -w//2+1, ends replaced by growing-window medians
+			for (int i = lane; i < n; i += 32) {
+				double v;
+				if (i < ne) v = nanmedian_small(raw, 0, min(n, i + 2));
+				else if (i >= n - ne) v = nanmedian_small(raw, max(0, n - ((n - 1 - i) + 2)), n);
+				else { const int src = i + k; v = nanmedian_small(raw, max(0, src - w + 1), src + 1); }
+				rsm.s2[i] = v;
+			}
+		} else if (lane == 0) {
+			// tiny profile: the end fix-ups overlap, reproduce the assignment order literally
+			for (int i = 0; i < n; ++i) { const int src = (i + k) % n; rsm.s2[i] = nanmedian_small(raw, max(0, src - w + 1), src + 1); }
+			for (int e = 0; e < ne; ++e) {
+				rsm.s2[e] = nanmedian_small(raw, 0, min(n, e + 2));
+				rsm.s2[n - 1 - e] = nanmedian_small(raw, max(0, n - (e + 2)), n);
+			}
 		}
 	} else {
-		for (int i = 0; i < n; ++i) s2[i] = raw[i];
+		for (int i = lane; i < n; i += 32) rsm.s2[i] = raw[i];
 	}
-	// knots
-	int m = 0;
-	double* kx = c.kx;
-	double* ky = rsm.ky;
-	for (int i = 0; i < n; ++i) {
-		if (s2[i] == s2[i]) {
-			kx[m] = ring_center(P, i);  // bins[1:] - step/2
-			ky[m] = s2[i];
-			++m;
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) s2g[i] = rsm.s2[i];
+	// knots = finite ring values at the ring centres
+	if (lane == 0) {
+		int m = 0;
+		for (int i = 0; i < n; ++i) {
+			const double v = rsm.s2[i];
+			if (v == v) { rsm.kx[m] = ring_center(P, i); rsm.ky[m] = v; ++m; }
 		}
+		rsm.m = m;
 	}
+	__syncwarp();
+	const int m = rsm.m;
+	const double *kx = rsm.kx, *ky = rsm.ky;
 	int ok = 0;
 	if (m >= 4) {
-		// second derivatives M_i of the not-a-knot cubic interpolant
 		double *h = rsm.h, *dl = rsm.dl, *dg = rsm.dg, *du = rsm.du, *rhs = rsm.rhs, *M2 = rsm.M2;
-		for (int i = 0; i < m - 1; ++i) h[i] = kx[i + 1] - kx[i];
-		const int nu = m - 2;  // unknowns M_1 .. M_{m-2}
-		for (int i = 1; i <= nu; ++i) {
+		for (int i = lane; i < m - 1; i += 32) h[i] = kx[i + 1] - kx[i];
+		__syncwarp();
+		const int nu = m - 2;  // unknowns M_1 .. M_{m-2} (second derivatives of the not-a-knot cubic interpolant)
+		for (int i = 1 + lane; i <= nu; i += 32) {
 			dl[i] = h[i - 1]; dg[i] = 2.0 * (h[i - 1] + h[i]); du[i] = h[i];
 			rhs[i] = 6.0 * ((ky[i + 1] - ky[i]) / h[i] - (ky[i] - ky[i - 1]) / h[i - 1]);
 		}
-		// not-a-knot: M_0 = (1 + h0/h1) M_1 - (h0/h1) M_2 ; M_{m-1} likewise
-		{
+		__syncwarp();
+		if (lane == 0) {
+			// not-a-knot: M_0 = (1 + h0/h1) M_1 - (h0/h1) M_2 ; M_{m-1} likewise
 			const double r0 = h[0] / h[1];
 			dg[1] += dl[1] * (1.0 + r0);
 			du[1] -= dl[1] * r0;
 			const double r1 = h[m - 2] / h[m - 3];
 			dg[nu] += du[nu] * (1.0 + r1);
 			dl[nu] -= du[nu] * r1;
+			for (int i = 2; i <= nu; ++i) {   // Thomas algorithm
+				const double f = dl[i] / dg[i - 1];
+				dg[i] -= f * du[i - 1];
+				rhs[i] -= f * rhs[i - 1];
+			}
+			M2[nu] = rhs[nu] / dg[nu];
+			for (int i = nu - 1; i >= 1; --i) M2[i] = (rhs[i] - du[i] * M2[i + 1]) / dg[i];
+			M2[0] = (1.0 + r0) * M2[1] - r0 * M2[2];
+			M2[m - 1] = (1.0 + r1) * M2[m - 2] - r1 * M2[m - 3];
 		}
-		// Thomas algorithm
-		for (int i = 2; i <= nu; ++i) {
-			const double f = dl[i] / dg[i - 1];
-			dg[i] -= f * du[i - 1];
-			rhs[i] -= f * rhs[i - 1];
-		}
-		M2[nu] = rhs[nu] / dg[nu];
-		for (int i = nu - 1; i >= 1; --i) M2[i] = (rhs[i] - du[i] * M2[i + 1]) / dg[i];
-		M2[0] = (1.0 + h[0] / h[1]) * M2[1] - (h[0] / h[1]) * M2[2];
-		M2[m - 1] = (1.0 + h[m - 2] / h[m - 3]) * M2[m - 2] - (h[m - 2] / h[m - 3]) * M2[m - 3];
-		for (int i = 0; i < m - 1; ++i) {
+		__syncwarp();
+		for (int i = lane; i < m - 1; i += 32) {
+			c.kx[i] = kx[i];
 			c.pp[i][0] = ky[i];
 			c.pp[i][1] = (ky[i + 1] - ky[i]) / h[i] - h[i] * (2.0 * M2[i] + M2[i + 1]) / 6.0;
 			c.pp[i][2] = 0.5 * M2[i];
 			c.pp[i][3] = (M2[i + 1] - M2[i]) / (6.0 * h[i]);
 		}
-		// ring-centre interval -> spline piece
-		int s = 0;
-		for (int i = 0; i < n; ++i) {
+		if (lane == 0) c.kx[m - 1] = kx[m - 1];
+		// dense table: ring-centre interval -> covering spline piece
+		for (int i = lane; i < n; i += 32) {
 			const double cen = ring_center(P, i);
-			while (s + 1 < m - 1 && kx[s + 1] <= cen) ++s;
-			c.seg_of_ring[i] = (short)s;
-			c.seg[i][0] = kx[s];
-			for (int q = 0; q < 4; ++q) c.seg[i][1 + q] = c.pp[s][q];
+			int sidx = 0;
+			while (sidx + 1 < m - 1 && kx[sidx + 1] <= cen) ++sidx;
+			c.seg_of_ring[i] = (short)sidx;
+			c.seg[i][0] = kx[sidx];
+			c.seg[i][1] = ky[sidx];
+			c.seg[i][2] = (ky[sidx + 1] - ky[sidx]) / h[sidx] - h[sidx] * (2.0 * M2[sidx] + M2[sidx + 1]) / 6.0;
+			c.seg[i][3] = 0.5 * M2[sidx];
+			c.seg[i][4] = (M2[sidx + 1] - M2[sidx]) / (6.0 * h[sidx]);
 		}
-		c.x0 = kx[0]; c.xlast = kx[m - 1];
-		c.c_flat = exp10(ky[0]) - c.zp;
+		if (lane == 0) { c.x0 = kx[0]; c.xlast = kx[m - 1]; c.c_flat = exp10(ky[0]) - c.zp; }
 		ok = 1;
 	}
 	// m == 3: FITPACK raises "m must be > k" (caught, backgrounds.py:192-194); m < 3: not enough points.
-	c.radial_ok = ok;
-	c.npts = m;
-	if (!ok) c.c_flat = 0.0;
-	if (status) {
-		status[b].n_ring_valid[round] = m;
-		status[b].radial_ok[round] = ok;
-		status[b].zeropoint[round] = c.zp;
+	if (lane == 0) {
+		c.radial_ok = ok;
+		c.npts = m;
+		if (!ok) c.c_flat = 0.0;
+		if (status) {
+			status[b].n_ring_valid[round] = m;
+			status[b].radial_ok[round] = ok;
+			status[b].zeropoint[round] = c.zp;
+		}
 	}
 }
 
@@ -1388,17 +1412,16 @@ __global__ void __launch_bounds__(TBK_NT, 4) k_final(PlanDev P, Workspace ws,
 	const bool nonflat = P.use_radial && c.radial_ok && P.tile_slot[tile] >= 0;
 	if (nonflat) radial_stage(rs, c, P);
 	__syncthreads();
-	if (tid == 0) {
-		double cmin = INFINITY, cmax = -INFINITY;
-		for (int a = 0; a < 5; ++a) for (int bb = 0; bb < 5; ++bb) { cmin = fmin(cmin, z.c[a][bb]); cmax = fmax(cmax, z.c[a][bb]); }
+	if (tid < 32) {
+		double cmin = tid < 25 ? z.c[tid / 5][tid % 5] : INFINITY, cmax = tid < 25 ? z.c[tid / 5][tid % 5] : -INFINITY;
+		for (int o = 16; o > 0; o >>= 1) { cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); }
+		if (tid == 0) {
 		z.mesh_min = c.mesh_min; z.mesh_max = c.mesh_max; z.mesh_const = c.mesh_const;
 		z.radial_ok = c.radial_ok; z.c_flat = c.c_flat;
 		// small margin: the interpolated value can leave [cmin, cmax] only by rounding
 		const double eps = 1e-12 * fmax(fabs(cmin), fabs(cmax));
 		z.need_clip = !(cmin - eps >= c.mesh_min && cmax + eps <= c.mesh_max);
-		if (c.mesh_const) {  // ptp(mesh) == 0: the map is the constant (BkgZoomInterpolator short-circuit)
-			for (int a = 0; a < 5; ++a) for (int bb = 0; bb < 6; ++bb) z.c[a][bb] = c.mesh_min;
-			z.need_clip = 1;
+		if (c.mesh_const) z.need_clip = 1;   // ptp(mesh) == 0: the clip returns the constant (BkgZoomInterpolator short-circuit)
 		}
 	}
 	__syncthreads();
