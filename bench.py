@@ -339,7 +339,7 @@ def main():
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--ffis', type=int, default=1340, help='FFIs per GPU per step')
-	ap.add_argument('--chunk', type=int, default=32, help='FFIs per tbk_fit_batch launch')
+	ap.add_argument('--chunk', type=int, default=64, help='FFIs per tbk_fit_batch launch')
 	ap.add_argument('--streams', type=int, default=2, help='CUDA streams the chunks alternate between')
 	ap.add_argument('--e2e-ffis', type=int, default=512, help='pinned host stack size for the end-to-end leg')
 	ap.add_argument('--e2e-chunk', type=int, default=16)
