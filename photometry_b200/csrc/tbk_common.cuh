@@ -55,6 +55,8 @@ struct FfiCtl {
 	int radial_ok;              // current round: spline available
 	int npts;                   // spline knots
 	int mesh_const;             // ptp(mesh) == 0
+	int kde_fallbacks;          // diagnostics: quartile ranks resolved by the generic iterated selection
+	int pad0;
 	unsigned long long min_key; // rounds >= 2: ordered key of min(x - sq)
 	unsigned long long min_ub;  // rounds >= 2: ordered key of an upper bound of that minimum (pruning)
 	double zp;                  // zeropoint of the current round

@@ -20,6 +20,7 @@ __global__ void k_init_ctl(PlanDev P, Workspace ws, const tbk_ffi_meta* __restri
 	c.radial_ok = 0;
 	c.npts = 0;
 	c.mesh_const = 0;
+	c.kde_fallbacks = 0;
 	c.min_key = ~0ULL;
 	c.min_ub = ~0ULL;
 	c.zp = 0.0; c.c_flat = 0.0; c.x0 = 0.0; c.xlast = 0.0;
@@ -816,6 +817,7 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 		for (int r = 0; r < 4; ++r) {
 			if (done[r]) continue;
 			if (r > 0 && rk[r] == rk[r - 1]) { ord[r] = ord[r - 1]; continue; }
+			if (tid == 0) atomicAdd(const_cast<int*>(&c.kde_fallbacks), 1);
 			ord[r] = block_select(sm.sel, sm.red, each, rk[r], mn, mx);
 		}
 		for (int t = 0; t < 2; ++t) {
