@@ -33,7 +33,7 @@ TILESTAT_DTYPE = np.dtype([('mean', '<f8'), ('med', '<f8'), ('std', '<f8'), ('nf
 CTL_DTYPE = np.dtype([('min_bits', '<u4'), ('any_nonzero', '<i4'), ('n_valid', '<i4'), ('mars', '<i4'), ('earth', '<i4'),
 	('all_masked', '<i4'), ('no_good_mesh', '<i4'), ('radial_ok', '<i4'), ('npts', '<i4'), ('mesh_const', '<i4'), ('kde_fallbacks', '<i4'), ('pad0', '<i4'),
 	('min_key', '<u8'), ('min_ub', '<u8'), ('zp', '<f8'), ('c_flat', '<f8'), ('x0', '<f8'), ('xlast', '<f8'), ('mesh_min', '<f8'), ('mesh_max', '<f8'),
-	('kx', '<f8', (128,)), ('pp', '<f8', (128, 4)), ('seg', '<f8', (128, 5)), ('seg_of_ring', '<i2', (128,))])
+	('kx', '<f8', (128,)), ('pp', '<f8', (128, 4)), ('seg', '<f8', (128, 6)), ('seg_of_ring', '<i2', (128,))])
 
 # name -> (restype, argtypes); every symbol include/tbk.h declares
 _p = C.c_void_p

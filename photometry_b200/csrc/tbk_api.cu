@@ -149,6 +149,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 
 	std::vector<int> ring_ptr(1, 0), ring_pix, nonflat, tile_slot(P.ntiles, -1), ringtile_id, ringtile_ptr(1, 0);
 	std::vector<unsigned> ringtile_ent;
+	std::vector<double> nonflat_r;
 	if (P.use_radial) {
 		// backgrounds.py:145-154
 		std::vector<double> r((size_t)H * W);
@@ -220,6 +221,12 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 			if (m > c0) { tile_slot[t] = (int)nonflat.size(); nonflat.push_back(t); }
 		}
 		P.n_nonflat = (int)nonflat.size();
+		nonflat_r.resize((size_t)nonflat.size() * TBK_NPIX_TILE);
+		for (size_t k = 0; k < nonflat.size(); ++k) {
+			const int ty = nonflat[k] / P.nx, tx = nonflat[k] % P.nx;
+			for (int a = 0; a < TBK_TILE; ++a) for (int bb = 0; bb < TBK_TILE; ++bb)
+				nonflat_r[k * TBK_NPIX_TILE + a * TBK_TILE + bb] = r[(size_t)(ty * TBK_TILE + a) * W + tx * TBK_TILE + bb];
+		}
 	}
 	// cubic B-spline weights per sub-tile phase (scipy ni_interpolation.c, order 3):
 	// output o samples u = (o + 0.5)/64 - 0.5; x = u - floor(u)
@@ -243,7 +250,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	if ((rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
 		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
 		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle)) ||
-		(rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
+		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
 		tbk_plan_destroy(p);
 		return rc;
 	}

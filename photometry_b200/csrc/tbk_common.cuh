@@ -29,6 +29,7 @@ struct PlanDev {
 	const int* ring_pix;        // [nringpix] (y << 16) | x, row-major within a ring
 	const int* nonflat_tiles;   // [n_nonflat] tile ids
 	const int* tile_slot;       // [ntiles] index into nonflat list or -1 (flat tile)
+	const double* nonflat_r;    // [n_nonflat][64*64] pixel radius of the non-flat meshes (static, bit-equal to pixel_radius)
 	int n_ringtiles;            // meshes that contain at least one ring pixel
 	const int* ringtile_id;     // [n_ringtiles] mesh id
 	const int* ringtile_ptr;    // [n_ringtiles + 1] CSR offsets into ringtile_ent
@@ -65,7 +66,7 @@ struct FfiCtl {
 	double mesh_min, mesh_max;
 	double kx[TBK_MAX_RINGS];       // knot abscissae
 	double pp[TBK_MAX_RINGS][4];    // piecewise cubic: y = pp0 + s*(pp1 + s*(pp2 + s*pp3)), s = t - kx[i]
-	double seg[TBK_MAX_RINGS][5];   // dense table per ring-centre interval: {knot, pp0..pp3} of the covering piece
+	double seg[TBK_MAX_RINGS][6];   // dense table per ring-centre interval: {knot, pp0..pp3, 10**pp0} of the covering piece
 	short seg_of_ring[TBK_MAX_RINGS]; // ring-centre interval -> spline piece
 };
 
@@ -143,7 +144,7 @@ __device__ __forceinline__ double radial_value(const FfiCtl& c, const PlanDev& P
 // Shared-memory copy of the per-FFI radial profile for kernels that evaluate it per pixel: the dense
 // ring-centre-interval table makes the piece lookup one multiply + one conversion (no search).
 struct RadialSmem2 {
-	double seg[TBK_MAX_RINGS][5];
+	double seg[TBK_MAX_RINGS][6];
 	double x0, xlast, c_flat, zp, center0, inv_step;
 	int radial_ok, nseg;
 };
@@ -151,7 +152,7 @@ struct RadialSmem2 {
 __device__ __forceinline__ void radial_stage(RadialSmem2& rs, const FfiCtl& c, const PlanDev& P)
 {
 	const int nseg = max(P.nrings - 1, 1);
-	for (int i = threadIdx.x; i < nseg * 5; i += blockDim.x) rs.seg[i / 5][i % 5] = c.seg[i / 5][i % 5];
+	for (int i = threadIdx.x; i < nseg * 6; i += blockDim.x) rs.seg[i / 6][i % 6] = c.seg[i / 6][i % 6];
 	if (threadIdx.x == 0) {
 		rs.x0 = c.x0; rs.xlast = c.xlast; rs.c_flat = c.c_flat; rs.zp = c.zp;
 		rs.center0 = ring_center(P, 0); rs.inv_step = 1.0 / P.step;
@@ -159,6 +160,9 @@ __device__ __forceinline__ void radial_stage(RadialSmem2& rs, const FfiCtl& c, c
 	}
 }
 
+// 10**spline(clamp(r)) - zp.  Within a piece y = y_i + dy with |dy| small, so 10**y = 10**y_i * exp(ln10 dy):
+// the table holds 10**y_i and exp() is a degree-9 Taylor polynomial (relative error < 1e-16 for |ln10 dy| < 0.1;
+// steeper profiles take the exp10 path).
 __device__ __forceinline__ double radial_value_s(const RadialSmem2& rs, double r)
 {
 	if (!rs.radial_ok) return 0.0;
@@ -167,8 +171,13 @@ __device__ __forceinline__ double radial_value_s(const RadialSmem2& rs, double r
 	const int i = max(0, min(rs.nseg - 1, (int)((t - rs.center0) * rs.inv_step)));
 	const double* e = rs.seg[i];
 	const double u = t - e[0];
-	const double y = e[1] + u * (e[2] + u * (e[3] + u * e[4]));
-	return exp10(y) - rs.zp;
+	const double dy = u * (e[2] + u * (e[3] + u * e[4]));
+	const double x = 2.302585092994045684 * dy;
+	if (fabs(x) > 0.1) return exp10(e[1] + dy) - rs.zp;
+	double p = 1.0 / 362880.0;
+	p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0); p = fma(p, x, 1.0 / 720.0); p = fma(p, x, 1.0 / 120.0);
+	p = fma(p, x, 1.0 / 24.0); p = fma(p, x, 1.0 / 6.0); p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
+	return e[5] * p - rs.zp;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1092,6 +1092,7 @@ __global__ void __launch_bounds__(32) k_radial_fit(PlanDev P, Workspace ws, tbk_
 			c.seg[i][2] = (ky[sidx + 1] - ky[sidx]) / h[sidx] - h[sidx] * (2.0 * M2[sidx] + M2[sidx + 1]) / 6.0;
 			c.seg[i][3] = 0.5 * M2[sidx];
 			c.seg[i][4] = (M2[sidx + 1] - M2[sidx]) / (6.0 * h[sidx]);
+			c.seg[i][5] = exp10(ky[sidx]);
 		}
 		if (lane == 0) { c.x0 = kx[0]; c.xlast = kx[m - 1]; c.c_flat = exp10(ky[0]) - c.zp; }
 		ok = 1;
@@ -1180,10 +1181,13 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
 		const unsigned int m = __ldg(reinterpret_cast<const unsigned int*>(mask + off));
 		const float x4[4] = {x.x, x.y, x.z, x.w};
+		const double2 r01 = __ldg(reinterpret_cast<const double2*>(P.nonflat_r + (size_t)slot * TBK_NPIX_TILE + lrow * TBK_TILE + lcol));
+		const double2 r23 = __ldg(reinterpret_cast<const double2*>(P.nonflat_r + (size_t)slot * TBK_NPIX_TILE + lrow * TBK_TILE + lcol + 2));
+		const double rr[4] = {r01.x, r01.y, r23.x, r23.y};
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			unsigned long long k = ~0ULL;
-			if (!((m >> (8 * q)) & 0xFFu)) { k = dkey((double)x4[q] - radial_value_s(rs, pixel_radius(P, gy, gx + q))); ++n; }
+			if (!((m >> (8 * q)) & 0xFFu)) { k = dkey((double)x4[q] - radial_value_s(rs, rr[q])); ++n; }
 			sm.tw.keys[lrow * TBK_TILE + lcol + q] = k;
 		}
 	}
@@ -1373,11 +1377,17 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, const RadialSmem2
 			for (int b = 0; b < 4; ++b) r[b] = fma(wy, z.c[oy + a][ox + b], r[b]);
 		}
 		float o[4];
+		double rr[4] = {0.0, 0.0, 0.0, 0.0};
+		if (NONFLAT) {
+			const double* rp = P.nonflat_r + (size_t)P.tile_slot[ty * P.nx + tx] * TBK_NPIX_TILE + lrow * TBK_TILE + lcol;
+			const double2 r01 = __ldg(reinterpret_cast<const double2*>(rp)), r23 = __ldg(reinterpret_cast<const double2*>(rp + 2));
+			rr[0] = r01.x; rr[1] = r01.y; rr[2] = r23.x; rr[3] = r23.y;
+		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			double sq = wx[q][0] * r[0] + wx[q][1] * r[1] + wx[q][2] * r[2] + wx[q][3] * r[3];
 			if (CLIP) sq = fmin(fmax(sq, lo), hi);
-			const double rad = NONFLAT ? radial_value_s(rs, pixel_radius(P, gy, gx + q)) : cflat;
+			const double rad = NONFLAT ? radial_value_s(rs, rr[q]) : cflat;
 			o[q] = (float)(rad + sq);
 		}
 		*reinterpret_cast<float4*>(bkg + img + (size_t)gy * P.W + gx) = make_float4(o[0], o[1], o[2], o[3]);
