@@ -306,11 +306,22 @@ __global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Wo
 	__syncthreads();
 	uint32_t nz = 0u;
 	int nbad = 0;
+	// all of this thread's pixels are fetched at once with cp.async (16 B each) into the key buffer, so the
+	// HBM latency is paid once per mesh; every thread later reads back only what it copied itself
+	{
+#pragma unroll
+		for (int i = 0; i < 8 * LPA; ++i) {
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.tw.keys[(lrow0 + 2 * NW * i) * TBK_TILE + lcol]);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(cube + base + (size_t)i * step));
+		}
+		asm volatile("cp.async.commit_group;");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+	}
 #pragma unroll 1
 	for (int a = 0; a < 8; ++a) {   // rows 8a .. 8a+7 of the mesh: loads 2a and 2a+1 of both warps
 		float4 r[LPA];
 #pragma unroll
-		for (int h = 0; h < LPA; ++h) r[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(LPA * a + h) * step));
+		for (int h = 0; h < LPA; ++h) r[h] = *reinterpret_cast<const float4*>(&sm.tw.keys[(lrow0 + 2 * NW * (LPA * a + h)) * TBK_TILE + lcol]);
 		uint32_t smin = TW_INVALID;
 #pragma unroll
 		for (int h = 0; h < LPA; ++h) {
