@@ -1185,20 +1185,32 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 	if (tid == 0) s_n = 0;
 	__syncthreads();
 	int n = 0;
+	// rolled (the radial evaluation is ~100 instructions per pixel) with the next step's loads issued ahead
+	const size_t img = (size_t)b * P.H * P.W;
+	const double* rbase = P.nonflat_r + (size_t)slot * TBK_NPIX_TILE;
+	const int lrow_first = 2 * w + (lane >> 4);
+	float4 x = __ldg(reinterpret_cast<const float4*>(cube + img + (size_t)(ty * TBK_TILE + lrow_first) * P.W + gx));
+	unsigned int m = __ldg(reinterpret_cast<const unsigned int*>(mask + img + (size_t)(ty * TBK_TILE + lrow_first) * P.W + gx));
+	double2 r01 = __ldg(reinterpret_cast<const double2*>(rbase + lrow_first * TBK_TILE + lcol));
+	double2 r23 = __ldg(reinterpret_cast<const double2*>(rbase + lrow_first * TBK_TILE + lcol + 2));
 #pragma unroll 1
-	for (int i = 0; i < 8; ++i) {   // rolled: the radial evaluation is ~150 instructions per pixel
-		const int lrow = 8 * i + 2 * w + (lane >> 4), gy = ty * TBK_TILE + lrow;
-		const size_t off = (size_t)b * P.H * P.W + (size_t)gy * P.W + gx;
-		const float4 x = __ldg(reinterpret_cast<const float4*>(cube + off));
-		const unsigned int m = __ldg(reinterpret_cast<const unsigned int*>(mask + off));
+	for (int i = 0; i < 8; ++i) {
+		const int lrow = 8 * i + lrow_first;
 		const float x4[4] = {x.x, x.y, x.z, x.w};
-		const double2 r01 = __ldg(reinterpret_cast<const double2*>(P.nonflat_r + (size_t)slot * TBK_NPIX_TILE + lrow * TBK_TILE + lcol));
-		const double2 r23 = __ldg(reinterpret_cast<const double2*>(P.nonflat_r + (size_t)slot * TBK_NPIX_TILE + lrow * TBK_TILE + lcol + 2));
 		const double rr[4] = {r01.x, r01.y, r23.x, r23.y};
+		const unsigned int mcur = m;
+		if (i < 7) {
+			const int lnext = lrow + 8;
+			const size_t off = img + (size_t)(ty * TBK_TILE + lnext) * P.W + gx;
+			x = __ldg(reinterpret_cast<const float4*>(cube + off));
+			m = __ldg(reinterpret_cast<const unsigned int*>(mask + off));
+			r01 = __ldg(reinterpret_cast<const double2*>(rbase + lnext * TBK_TILE + lcol));
+			r23 = __ldg(reinterpret_cast<const double2*>(rbase + lnext * TBK_TILE + lcol + 2));
+		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			unsigned long long k = ~0ULL;
-			if (!((m >> (8 * q)) & 0xFFu)) { k = dkey((double)x4[q] - radial_value_s(rs, rr[q])); ++n; }
+			if (!((mcur >> (8 * q)) & 0xFFu)) { k = dkey((double)x4[q] - radial_value_s(rs, rr[q])); ++n; }
 			sm.tw.keys[lrow * TBK_TILE + lcol + q] = k;
 		}
 	}
