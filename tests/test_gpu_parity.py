@@ -392,3 +392,26 @@ def test_more_parameter_variants(kw):
 	case = CASES['tess_small']()
 	kw2 = dict(case['fit_kwargs']); kw2.update(kw)
 	_compare_with_oracle(case['images'][1], case['headers'][1], xycen=case['xycen'], **kw2)
+
+
+@pytest.mark.parametrize('seed', list(range(40, 48)))
+def test_randomised_fields(seed):
+	"""Random backgrounds / star densities / NaN and mask fractions, TESS and non-TESS, against the live oracle."""
+	rng = np.random.default_rng(seed)
+	H, W = int(rng.choice([128, 192, 256])), int(rng.choice([192, 256, 320]))
+	level = float(rng.uniform(20, 3000))
+	img = level * (1 + 0.3 * rng.uniform(-1, 1) * np.linspace(-1, 1, W)[None, :] + 0.2 * rng.uniform(-1, 1) * np.linspace(-1, 1, H)[:, None])
+	img = img + rng.standard_normal((H, W)) * np.sqrt(img + 4)
+	nstar = int(rng.integers(0, 400))
+	ys, xs = rng.integers(0, H, nstar), rng.integers(0, W, nstar)
+	img[ys, xs] += 10 ** rng.uniform(1, 5.2, nstar)
+	img[rng.uniform(size=(H, W)) < rng.choice([0, 1e-3, 0.05])] = np.nan
+	img = img.astype('float32')
+	extra = (rng.uniform(size=(H, W)) < rng.choice([0, 0.2, 0.45])) if seed % 2 else None
+	if seed % 3 == 0:
+		_compare_with_oracle(img, extra=extra)
+	else:
+		xycen = (-float(rng.uniform(5, 40)), float(H + rng.uniform(10, 60)))
+		rmax = np.hypot(W + 44 - xycen[0], xycen[1])
+		_compare_with_oracle(img, header(int(rng.integers(1, 5)), int(rng.integers(1, 4)), 0), xycen=xycen, extra=extra,
+			radial_cutoff=float(0.75 * rmax), radial_pixel_step=float(rng.choice([8, 12, 15])), radial_smooth=int(rng.choice([0, 3, 5])))
