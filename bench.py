@@ -234,7 +234,7 @@ def run_b200(args):
 	launches_per_call = {'tile_base': 1, 'tile_round': 3, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
 	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
 	peak, peak_src = load_peaks()
-	# The fit is a chain of 17 kernel launches per batch and no single kernel dominates (the largest is < 30 % of
+	# The fit is a chain of 25 kernel launches per batch and no single kernel dominates (the largest is < 30 % of
 	# the step), so the roofline is stated for the whole chain: algorithmic bytes of one tbk_fit_batch launch
 	# (37,748,736 B x FFIs per launch) over the summed device time of its kernels (CUDA events between the
 	# launches, tbk_fit_batch_profiled).  The dominant kernel is reported beside it with its share of the step.
@@ -252,7 +252,7 @@ def run_b200(args):
 				dom_traffic = (e['dram_read_bytes'] + e['dram_write_bytes']) / e['launches'] / prof_json['ffis_per_launch'] * min(chunk, n)
 	except (OSError, KeyError, ValueError):
 		pass
-	roofline = {"bound": "hbm", "kernel": "tbk_fit_batch (chain of 17 launches; sum of kernel device times)",
+	roofline = {"bound": "hbm", "kernel": "tbk_fit_batch (chain of 25 launches; sum of kernel device times)",
 		"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
 		"traffic_source": "profiles/r01_ncu_fit_summary.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum over the chain, scaled to this launch size)",
 		"peak_source": peak_src, "launch_ms": launch_ms, "ffis_per_launch": min(chunk, n),
