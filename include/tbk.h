@@ -133,6 +133,14 @@ int tbk_sum_finalize(tbk_plan* plan, const double* sum, const int32_t* nimg, con
 int tbk_debug_fetch(tbk_plan* plan, const void* workspace, int B, int b, int round,
 	double* s2, double* mesh);
 
+/*
+ * Ingest helper (io.py:46-48): decode B raw FITS image HDUs (big-endian float32, naxis2 rows of naxis1 pixels,
+ * contiguous per FFI, already on the device) into the science crop ``[row0:row0+H, col0:col0+W]`` as native
+ * float32 [B, H, W].  For TESS FFIs naxis1 = 2136, naxis2 = 2078, row0 = 0, col0 = 44, H = W = 2048.
+ */
+int tbk_decode_ffi_be(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W,
+	float* cube_out, void* stream);
+
 /* Kernel classes reported by tbk_fit_batch_profiled (milliseconds per class, summed over rounds). */
 enum {
 	TBK_K_TILE_BASE = 0,   /* mask build + sigma-clipped statistics of every mesh */

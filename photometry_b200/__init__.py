@@ -7,5 +7,6 @@ from .backgrounds import fit_background, BackgroundFitter, make_meta, meta_from_
 from .io import FFIImage  # noqa: F401
 from .quality import TESSQualityFlags, PixelQualityFlags  # noqa: F401
 from .prepare import prepare_stack, fit_stack_host, SectorResult  # noqa: F401
+from .ingest import load_ffi_stack, decode_ffi_be  # noqa: F401
 
 __version__ = '0.1.0'

@@ -355,3 +355,13 @@ extern "C" int tbk_workspace_layout(const tbk_plan* p, int B, size_t* offsets, s
 	sizes[0] = sizeof(FfiCtl); sizes[1] = sizeof(TileStat); sizes[2] = (size_t)p->dev.n_nonflat;
 	return TBK_OK;
 }
+
+extern "C" int tbk_decode_ffi_be(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W,
+	float* cube_out, void* stream)
+{
+	if (!raw || !cube_out || B <= 0 || H <= 0 || W <= 0 || W % 4 || row0 < 0 || col0 < 0 || row0 + H > naxis2 || col0 + W > naxis1
+		|| ((uintptr_t)raw & 3) || ((uintptr_t)cube_out & 15) || H > 65535 || B > 65535) {
+		tbk_set_error("tbk_decode_ffi_be: bad argument"); return TBK_ERR_INVALID;
+	}
+	return tbk_launch_decode(raw, B, naxis1, naxis2, row0, col0, H, W, cube_out, (cudaStream_t)stream);
+}

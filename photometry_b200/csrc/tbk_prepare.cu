@@ -158,3 +158,36 @@ int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg
 	if (e != cudaSuccess) { tbk_set_error("k_sum_finalize: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
 	return TBK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// FITS image HDU (big-endian float32) -> native float32 science crop (io.py:46-48).  One thread per output
+// float4; the source row is only 4-byte aligned (col0 = 44 pixels = 176 bytes is, the row pitch 8544 bytes is
+// 16-byte aligned, so 128-bit loads are fine whenever col0 % 4 == 0; otherwise scalar loads).
+__global__ void __launch_bounds__(256) k_decode_ffi_be(const uint32_t* __restrict__ raw, int naxis1, size_t hdu_words,
+	int row0, int col0, int H, int W, float* __restrict__ out)
+{
+	const int b = blockIdx.z, y = blockIdx.y;
+	const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (x >= W) return;
+	const uint32_t* src = raw + (size_t)b * hdu_words + (size_t)(row0 + y) * naxis1 + col0 + x;
+	uint32_t w[4];
+	if ((((uintptr_t)src) & 15) == 0) {
+		const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+		w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+	} else {
+		for (int q = 0; q < 4; ++q) w[q] = __ldg(src + q);
+	}
+	float4 o;
+	o.x = __uint_as_float(__byte_perm(w[0], 0, 0x0123)); o.y = __uint_as_float(__byte_perm(w[1], 0, 0x0123));
+	o.z = __uint_as_float(__byte_perm(w[2], 0, 0x0123)); o.w = __uint_as_float(__byte_perm(w[3], 0, 0x0123));
+	*reinterpret_cast<float4*>(out + ((size_t)b * H + y) * W + x) = o;
+}
+
+int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W, float* out, cudaStream_t st)
+{
+	dim3 grid((W / 4 + 255) / 256, H, B);
+	k_decode_ffi_be<<<grid, 256, 0, st>>>((const uint32_t*)raw, naxis1, (size_t)naxis1 * naxis2, row0, col0, H, W, out);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_decode_ffi_be: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}

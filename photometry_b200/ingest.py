@@ -1,0 +1,60 @@
+"""
+Input side of the hot path (SURVEY 8f "next" #2): TESS FFI FITS(.gz) files -> device-resident float32 cube.
+
+The reference decodes every file twice on the host (gunzip + FITS parse + big-endian -> native + crop,
+photometry/io.py:37-52, called from backgrounds.py:86 and again from prepare.py:379).  Here the host only
+inflates the file and parses the header cards (thread pool; zlib releases the GIL); the raw big-endian image HDU
+goes to the device through a pinned staging buffer and ``tbk_decode_ffi_be`` byte-swaps and crops
+``[0:2048, 44:2092]`` straight into the cube.
+"""
+import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
+import numpy as np
+import torch
+from . import _lib
+from .io import read_ffi_raw
+
+
+def decode_ffi_be(raw_dev, B, naxis1, naxis2, out, row0=0, col0=44):
+	"""Device decode of B raw image HDUs (uint8 CUDA tensor) into ``out`` float32 [B, H, W]."""
+	lib = _lib.load()
+	H, W = out.shape[1:]
+	stream = torch.cuda.current_stream(out.device).cuda_stream
+	_lib.check(lib.tbk_decode_ffi_be(C.c_void_p(raw_dev.data_ptr()), int(B), int(naxis1), int(naxis2), int(row0), int(col0),
+		int(H), int(W), C.c_void_p(out.data_ptr()), C.c_void_p(stream)), 'tbk_decode_ffi_be')
+	return out
+
+
+def load_ffi_stack(paths, device=None, threads=8, batch=8):
+	"""
+	Read the FFIs in ``paths`` (time ordered) into a CUDA tensor float32 [N, 2048, 2048].
+	Returns ``(cube, headers)``; ``photometry_b200.meta_from_headers(headers)`` gives the per-FFI meta.
+	"""
+	if not torch.cuda.is_available():
+		raise _lib.TbkError("CUDA device required: photometry_b200 has no CPU fallback")
+	device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+	n = len(paths)
+	H = W = 2048
+	cube = torch.empty((n, H, W), dtype=torch.float32, device=device)
+	headers = [None] * n
+	hdu_bytes = 2136 * 2078 * 4
+	stage = [torch.empty((batch, hdu_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
+	stage_dev = [torch.empty((batch, hdu_bytes), dtype=torch.uint8, device=device) for _ in range(2)]
+	done = [torch.cuda.Event(), torch.cuda.Event()]
+	with ThreadPoolExecutor(max_workers=threads) as pool:
+		it = pool.map(read_ffi_raw, paths)
+		for bi, a in enumerate(range(0, n, batch)):
+			b = min(a + batch, n)
+			k = bi & 1
+			if bi >= 2:
+				done[k].synchronize()   # the staging buffer must have been consumed
+			for j in range(a, b):
+				hdr, raw, n1, n2 = next(it)
+				if (n1, n2) != (2136, 2078):
+					raise ValueError(f"{paths[j]}: unexpected image size {n1} x {n2}")
+				headers[j] = hdr
+				stage[k].numpy()[j - a, :] = np.frombuffer(raw, dtype=np.uint8)
+			stage_dev[k][:b - a].copy_(stage[k][:b - a], non_blocking=True)
+			decode_ffi_be(stage_dev[k], b - a, 2136, 2078, cube[a:b])
+			done[k].record()
+	return cube, headers

@@ -44,6 +44,64 @@ def _parse_card(card):
 		return key, val
 
 
+def scan_fits(buf):
+	"""Yield (header dict, data offset, shape, bitpix) for every HDU of an in-memory FITS file."""
+	pos = 0
+	while pos + _BLOCK <= len(buf):
+		hdr = {}
+		done = False
+		while not done:
+			block = bytes(buf[pos:pos + _BLOCK]).decode('ascii', 'replace')
+			pos += _BLOCK
+			for i in range(0, _BLOCK, 80):
+				card = block[i:i + 80]
+				if card.startswith('END') and card[3:].strip() == '':
+					done = True
+					break
+				key, val = _parse_card(card)
+				if val is not None and key not in hdr:
+					hdr[key] = val
+			if pos >= len(buf) and not done:
+				raise ValueError("truncated FITS header")
+		naxis = int(hdr.get('NAXIS', 0))
+		shape = [int(hdr[f'NAXIS{i}']) for i in range(naxis, 0, -1)]
+		bitpix = int(hdr.get('BITPIX', 8))
+		nbytes = abs(bitpix) // 8 * int(np.prod(shape)) if naxis else 0
+		nbytes = (nbytes + int(hdr.get('PCOUNT', 0))) * int(hdr.get('GCOUNT', 1)) if naxis else 0
+		yield hdr, pos, shape, bitpix
+		pos += (nbytes + _BLOCK - 1) // _BLOCK * _BLOCK
+
+
+def read_ffi_raw(path):
+	"""
+	Read a TESS FFI FITS(.gz) file WITHOUT decoding the pixels: returns
+	``(merged header, raw big-endian bytes of the image HDU, naxis1, naxis2)`` for the device-side decode
+	(:func:`photometry_b200.ingest.load_ffi_stack`).  Raises ValueError for non-TESS files (io.py:46).
+	"""
+	opener = gzip.open if str(path).endswith('.gz') else open
+	with opener(path, 'rb') as fid:
+		buf = fid.read()
+	hdus = []
+	for item in scan_fits(buf):
+		hdus.append(item)
+		if len(hdus) == 2:
+			break
+	if len(hdus) < 2:
+		raise ValueError(f"{path}: no image extension")
+	hdr0, (hdr1, off, shape, bitpix) = hdus[0][0], hdus[1]
+	if hdr0.get('TELESCOP') != 'TESS' or hdr1.get('NAXIS1') != 2136 or hdr1.get('NAXIS2') != 2078 or bitpix != -32:
+		raise ValueError(f"{path}: not a TESS full-frame image")
+	hdr = dict(hdr0)
+	hdr.update(hdr1)
+	if 'FFIINDEX' not in hdr and hdr['EXPOSURE'] * 86400 > 1000:
+		time = 0.5 * (hdr['TSTART'] + hdr['TSTOP'])
+		first_time = 0.5 * (1325.317007851970 + 1325.337841177751) - 3.9072474e-03
+		timedelt = 1800 / 86400
+		hdr['FFIINDEX'] = np.round((time - hdr.get('BARYCORR', 0)) / timedelt + (4697 - first_time / timedelt))
+	n1, n2 = shape[1], shape[0]
+	return hdr, memoryview(buf)[off:off + 4 * n1 * n2], n1, n2
+
+
 def read_fits_hdus(path):
 	"""Return [(header dict, ndarray or None), ...] for the primary HDU and image extensions."""
 	opener = gzip.open if str(path).endswith('.gz') else open

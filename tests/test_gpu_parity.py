@@ -415,3 +415,36 @@ def test_randomised_fields(seed):
 		rmax = np.hypot(W + 44 - xycen[0], xycen[1])
 		_compare_with_oracle(img, header(int(rng.integers(1, 5)), int(rng.integers(1, 4)), 0), xycen=xycen, extra=extra,
 			radial_cutoff=float(0.75 * rmax), radial_pixel_step=float(rng.choice([8, 12, 15])), radial_smooth=int(rng.choice([0, 3, 5])))
+
+
+# ---- input side: FITS(.gz) -> device cube ----------------------------------------------------------
+def test_load_ffi_stack_from_fits(tmp_path):
+	"""Device-side big-endian decode + science crop equals the host decode of io.FFIImage (io.py:46-52)."""
+	import gzip
+	from test_host_logic import _hdu
+	from photometry_b200.io import FFIImage
+	rng = np.random.default_rng(12)
+	paths = []
+	for k in range(3):
+		raw = rng.normal(100 + k, 3, (2078, 2136)).astype('float32')
+		raw[5, 50] = np.nan
+		prim = _hdu([('SIMPLE', True), ('BITPIX', 8), ('NAXIS', 0), ('EXTEND', True), ('TELESCOP', 'TESS'), ('CAMERA', 2), ('CCD', 3)])
+		ext = [('XTENSION', 'IMAGE'), ('BITPIX', -32), ('NAXIS', 2), ('NAXIS1', 2136), ('NAXIS2', 2078), ('PCOUNT', 0), ('GCOUNT', 1),
+			('TSTART', 1400.0 + 0.02 * k), ('TSTOP', 1400.02 + 0.02 * k), ('FFIINDEX', 9000 + k), ('DQUALITY', 0)]
+		blob = prim + _hdu(ext, raw) + _hdu(ext[:7], np.ones((2078, 2136), dtype='float32'))
+		path = str(tmp_path / f'tess2018{k:09d}-s0001-2-3-0120-s_ffic.fits') + ('.gz' if k != 1 else '')
+		with (gzip.open(path, 'wb', compresslevel=1) if path.endswith('.gz') else open(path, 'wb')) as fid:
+			fid.write(blob)
+		paths.append(path)
+	cube, headers = pb.load_ffi_stack(paths, threads=2, batch=2)
+	torch.cuda.synchronize()
+	assert cube.shape == (3, 2048, 2048) and cube.dtype == torch.float32
+	for k, path in enumerate(paths):
+		ref = FFIImage(path)
+		assert ref.is_tess
+		np.testing.assert_array_equal(cube[k].cpu().numpy(), ref.data)   # NaN == NaN by position in assert_array_equal
+		assert headers[k]['FFIINDEX'] == 9000 + k and headers[k]['CAMERA'] == 2 and headers[k]['CCD'] == 3
+	# and the stack runs through the fit
+	fit = pb.BackgroundFitter((2048, 2048), True, 2, 3)
+	bkg, mask, st = fit.fit(cube, pb.meta_from_headers(headers))
+	assert torch.isfinite(bkg).all() and int(mask[0, 5, 6]) == 1 and int(mask.sum()) == 3
