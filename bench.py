@@ -263,7 +263,7 @@ def run_b200(args):
 		"with_streams_achieved": value / world * ALGO_BYTES_PER_FFI / 1e9, "with_streams_frac": value / world * ALGO_BYTES_PER_FFI / 1e9 / peak}
 
 	# ---- end to end: pinned host stack -> device -> fit -> pinned host results (same metric)
-	ne = min(args.e2e_ffis, n)
+	ne = min(args.e2e_ffis, n, max(64, 2048 // world))   # keep the pinned host footprint bounded when 8 ranks share one host
 	host_in = torch.empty((ne, H, W), dtype=torch.float32).pin_memory()
 	host_in.copy_(cube[:ne])
 	host_bkg = torch.empty((ne, H, W), dtype=torch.float32).pin_memory()
