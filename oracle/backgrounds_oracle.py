@@ -452,6 +452,7 @@ def fit_background(image, catalog=None, flux_cutoff=8e4, bkgiters=3, radial_cuto
 		rd['mesh_unfiltered'] = bkg.mesh_unfiltered
 		rd['mesh_good'] = bkg.mesh_good
 		rd['n_excluded'] = bkg.n_excluded
+		rd['mesh_nbad'] = bkg.mesh_nbad
 		rd['clip_lo'], rd['clip_hi'] = bkg.clip_lo, bkg.clip_hi
 		diag['rounds'].append(rd)
 

@@ -191,7 +191,9 @@ class BackgroundFitter:
 		base = raw[offs[1]:offs[1] + B * self.ntiles * sizes[1]].view(_lib.TILESTAT_DTYPE).reshape(B, self.ntiles)
 		nf = raw[offs[2]:offs[2] + B * nnf * sizes[1]].view(_lib.TILESTAT_DTYPE).reshape(B, nnf)
 		coef = raw[offs[3]:offs[3] + B * self.ntiles * 8].view('<f8').reshape(B, self.ntiles)
-		return dict(ctl=ctl, tile_base=base, tile_nf=nf, coef=coef)
+		nr = max(self.nrings, 1)
+		s2_raw = raw[offs[5]:offs[5] + B * nr * 8].view('<f8').reshape(B, nr)[:, :self.nrings]
+		return dict(ctl=ctl, tile_base=base, tile_nf=nf, coef=coef, s2_raw=s2_raw)
 
 	# ------------------------------------------------------------------------------------------
 	def time_smooth(self, bkg, w, halo_lo=None, halo_hi=None, out=None):

@@ -1,6 +1,6 @@
 """Developer smoke check run on the GPU box: parity vs the oracle on a few cases + first timings."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import oracle
