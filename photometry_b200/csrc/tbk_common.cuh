@@ -160,6 +160,8 @@ __device__ __forceinline__ void radial_stage(RadialSmem2& rs, const FfiCtl& c, c
 	}
 }
 
+static __constant__ double c_exp_taylor[7] = {1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+
 // 10**spline(clamp(r)) - zp.  Within a piece y = y_i + dy with |dy| small, so 10**y = 10**y_i * exp(ln10 dy):
 // the table holds 10**y_i and exp() is a degree-9 Taylor polynomial (relative error < 1e-16 for |ln10 dy| < 0.1;
 // steeper profiles take the exp10 path).
@@ -174,10 +176,11 @@ __device__ __forceinline__ double radial_value_s(const RadialSmem2& rs, double r
 	const double dy = u * (e[2] + u * (e[3] + u * e[4]));
 	const double x = 2.302585092994045684 * dy;
 	if (fabs(x) > 0.1) return exp10(e[1] + dy) - rs.zp;
-	double p = 1.0 / 362880.0;
-	p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0); p = fma(p, x, 1.0 / 720.0); p = fma(p, x, 1.0 / 120.0);
-	p = fma(p, x, 1.0 / 24.0); p = fma(p, x, 1.0 / 6.0); p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
-	return e[5] * p - rs.zp;
+	// coefficients come from the constant bank (a DFMA operand) -- as literals each costs two moves per use
+	double p = c_exp_taylor[0];
+	p = fma(p, x, c_exp_taylor[1]); p = fma(p, x, c_exp_taylor[2]); p = fma(p, x, c_exp_taylor[3]); p = fma(p, x, c_exp_taylor[4]);
+	p = fma(p, x, c_exp_taylor[5]); p = fma(p, x, c_exp_taylor[6]); p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
+	return fma(e[5], p, -rs.zp);
 }
 
 // ---------------------------------------------------------------------------------------------

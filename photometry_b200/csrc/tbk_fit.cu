@@ -736,19 +736,23 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 		for (; i < hi; i += nt) { const double d = v[i]; if (d == d) f(d); }
 	};
 
-	int n = 0; double mn = INFINITY, mx = -INFINITY, s1 = 0.0, dmy = 0.0;
-	each([&](double d) { ++n; mn = fmin(mn, d); mx = fmax(mx, d); s1 += d; });
+	// n, min, max, mean and std(ddof=1) in one sweep: moments about a pivot sample (the first finite one among the
+	// leading entries), so the one-pass variance loses no more than a few ulps to cancellation
+	double pv = 0.0;
+	for (int t = 0; t < 4 && lo + 32 * t < hi; ++t) {
+		const int i = lo + 32 * t + (tid & 31);
+		const double d = i < hi ? v[i] : nan_d();
+		const unsigned fin = __ballot_sync(0xffffffffu, d == d);
+		if (fin) { pv = __shfl_sync(0xffffffffu, d, __ffs(fin) - 1); break; }
+	}
+	int n = 0; double mn = INFINITY, mx = -INFINITY, s1 = 0.0, ss = 0.0;
+	each([&](double d) { ++n; mn = fmin(mn, d); mx = fmax(mx, d); const double e = d - pv; s1 += e; ss = fma(e, e, ss); });
 	int nd = 0;
 	block_sum_min_max(sm.red, n, mn, mx);
-	block_sum3(sm.red, nd, s1, dmy);
+	block_sum3(sm.red, nd, s1, ss);
 	if (n <= 1) { if (tid == 0) *out = nan_d(); return; }  // reduce_mode([]) = NaN; one sample -> NaN
-
-	// std(ddof=1), two-pass like numpy
-	const double mean = s1 / (double)n;
-	double ss = 0.0; dmy = 0.0; nd = 0;
-	each([&](double d) { const double e = d - mean; ss += e * e; });
-	block_sum3(sm.red, nd, ss, dmy);
-	const double sd = sqrt(ss / (double)(n - 1));
+	const double mean = pv + s1 / (double)n;
+	const double sd = sqrt(fmax(ss - s1 * s1 / (double)n, 0.0) / (double)(n - 1));
 
 	// scipy.stats.scoreatpercentile(x, 25 / 75): linear interpolation at (n-1)*p.  The (up to) four order
 	// statistics are resolved together: one histogram over mean +- 1.8 std (which always brackets the
@@ -768,15 +772,33 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 		const bool fast = (w1 > w0) && (hscale < 1e300);
 		double ord[4];
 		bool done[4] = {false, false, false, false};
+		const int len = hi - lo;
+		const bool staged = len <= 8 * TBK_KDE_M;   // 16-bit bin per sample, overlaid on the (still unused) FFT buffer
+		uint16_t* sbin = reinterpret_cast<uint16_t*>(sm.x);
 		if (fast) {
 			for (int i = tid; i < TBK_NBINS; i += nt) sm.sel.hist[i] = 0u;
 			if (tid < 4) sm.qn[tid] = 0;
 			__syncthreads();
-			each([&](double d) {
+			auto binof = [&](double d) {
 				const double t = (d - w0) * hscale;
-				const int bin = d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
-				atomicAdd(&sm.sel.hist[bin], 1u);
-			});
+				return d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
+			};
+			if (staged) {
+				// the bin of every sample is kept (16 bit, 0xFFFF = masked) so the collecting sweep stays in shared memory
+				auto put = [&](int i, double d) {
+					int bin = 0xFFFF;
+					if (d == d) { bin = binof(d); atomicAdd(&sm.sel.hist[bin], 1u); }
+					sbin[i] = (uint16_t)bin;
+				};
+				int i = tid;
+				for (; i + 3 * nt < len; i += 4 * nt) {
+					const double d0 = v[lo + i], d1 = v[lo + i + nt], d2 = v[lo + i + 2 * nt], d3 = v[lo + i + 3 * nt];
+					put(i, d0); put(i + nt, d1); put(i + 2 * nt, d2); put(i + 3 * nt, d3);
+				}
+				for (; i < len; i += nt) put(i, v[lo + i]);
+			} else {
+				each([&](double d) { atomicAdd(&sm.sel.hist[binof(d)], 1u); });
+			}
 			__syncthreads();
 			// exclusive scan (thread t owns bins 2t, 2t+1 for 512 threads)
 			const int per = TBK_NBINS / TBK_KDE_NT;
@@ -800,15 +822,21 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 			// collect the members of the target bins (ranks in the same bin share list r of the first of them)
 			int lst[4];
 			for (int r = 0; r < 4; ++r) { lst[r] = r; for (int p = 0; p < r; ++p) if (qb[p] == qb[r]) { lst[r] = lst[p]; break; } }
-			each([&](double d) {
-				const double t = (d - w0) * hscale;
-				const int bin = d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
+			int tb[4];   // bins to collect (-1: nothing to do for this rank)
+			for (int r = 0; r < 4; ++r)
+				tb[r] = (lst[r] == r && qc[r] <= TBK_KDE_CAND && qb[r] != 0 && qb[r] != TBK_NBINS - 1) ? qb[r] : -1;
+			auto collect = [&](int bin, double d) {
 				for (int r = 0; r < 4; ++r)
-					if (lst[r] == r && bin == qb[r] && qc[r] <= TBK_KDE_CAND && bin != 0 && bin != TBK_NBINS - 1) {
-						const int p = atomicAdd(&sm.qn[r], 1);
-						sm.qcand[r][p] = d;
-					}
-			});
+					if (bin == tb[r]) { const int p = atomicAdd(&sm.qn[r], 1); sm.qcand[r][p] = d; }
+			};
+			if (staged) {
+				for (int i = tid; i < len; i += nt) {
+					const int bin = sbin[i];
+					if (bin == tb[0] || bin == tb[1] || bin == tb[2] || bin == tb[3]) collect(bin, v[lo + i]);
+				}
+			} else {
+				each([&](double d) { collect(binof(d), d); });
+			}
 			__syncthreads();
 			for (int r = 0; r < 4; ++r) {
 				const int L = lst[r];
@@ -864,10 +892,16 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 	if (fixed) { for (int i = tid; i < 4 * TBK_KDE_M; i += nt) lb[i] = 0u; }
 	else { for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i] = make_double2(0.0, 0.0); }
 	__syncthreads();
+	// (d - a) / delta as reciprocal multiply + one fma correction (= the correctly rounded quotient); a quotient
+	// that lands within 1e-9 of an integer is recomputed with the true division so the cell index cannot differ
+	const double rdelta = 1.0 / delta;
 	each([&](double d) {
-		const double lxi = (d - a) / delta;
-		const int li = (int)lxi;
-		const double rem = lxi - (double)li;
+		const double xa = d - a;
+		double lxi = xa * rdelta;
+		lxi = fma(fma(-lxi, delta, xa), rdelta, lxi);
+		int li = (int)lxi;
+		double rem = lxi - (double)li;
+		if (rem < 1e-9 || rem > 1.0 - 1e-9) { lxi = xa / delta; li = (int)lxi; rem = lxi - (double)li; }
 		if (li > 1 && li < TBK_KDE_M - 1) {
 			if (fixed) {
 				const unsigned long long fp = (unsigned long long)(rem * 281474976710656.0);  // rem * 2^48, rem in [0, 1)

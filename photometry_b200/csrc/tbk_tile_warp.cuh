@@ -37,7 +37,8 @@ struct TwBinMap {
 	float scale, off;
 };
 struct TwBinMap64 {
-	double scale, off, lo_c, hi_c;
+	double w0;              // window start; bins are laid over [w0, w0 + span]
+	float scale, lo, hi;    // bins per unit, clamp range of (value - w0)
 };
 
 // ---- key traits: float32 pixels (non-negative) and float64 residuals (any sign) ---------------
@@ -97,20 +98,25 @@ struct TwF64 {
 	__device__ static __forceinline__ K maxkey() { return 0xFFEFFFFFFFFFFFFFULL; }  // dkey(DBL_MAX)
 	__device__ static __forceinline__ K padkey() { return ~0ULL; }
 	__device__ static __forceinline__ double val(K k) { return dkey_inv(k); }
+	// Monotone non-decreasing map value -> bin.  Only the partition has to be monotone (membership tests inside
+	// a bin compare the float64 keys), so the offset from the window start is rounded to float32 and binned with
+	// one FFMA onto the 2^23 "magic" range like the float32 keys.
 	__device__ static __forceinline__ int bin(const Map& m, K k)
 	{
-		const double dc = fmin(fmax(dkey_inv(k), m.lo_c), m.hi_c);
-		const double t = fma(dc, m.scale, m.off);   // in [2^52 - 1, 2^52 + NB + 1]: integer spacing
-		const long long b = __double_as_longlong(t) - 0x4330000000000000LL;
-		return (int)max(0LL, min((long long)(TW_NB - 1), b));
+		const float e = (float)(dkey_inv(k) - m.w0);
+		const float t = fmaf(fminf(fmaxf(e, m.lo), m.hi), m.scale, 8388609.0f);   // 2^23 + 1 + [-1.5, NB - 0.5]
+		const int b = __float_as_int(t) - 0x4B000000;
+		return max(0, min(TW_NB - 1, b));
 	}
 	__device__ static __forceinline__ Map make_map(double w0, double w1)
 	{
 		Map bm;
-		bm.scale = (double)(TW_NB - 2) / (w1 - w0);
-		if (!(bm.scale < 1e300)) bm.scale = 1e300;
-		bm.lo_c = w0 - 1.5 / bm.scale; bm.hi_c = w1 + 1.5 / bm.scale;
-		bm.off = fma(-w0, bm.scale, 4503599627370497.0);  // 2^52 + 1
+		float span = (float)(w1 - w0);
+		if (!(span < 1e30f)) span = 1e30f;
+		bm.w0 = w0;
+		bm.scale = (float)(TW_NB - 2) / span;
+		if (!(bm.scale < 1e30f)) bm.scale = 1e30f;
+		bm.lo = -1.5f / bm.scale; bm.hi = span + 1.5f / bm.scale;
 		return bm;
 	}
 	__device__ static __forceinline__ double pivot_of(double med) { return med; }
