@@ -161,6 +161,10 @@ int tbk_fit_batch_profiled(tbk_plan* plan, const float* cube, int B, const tbk_f
 	const uint8_t* extra_mask, float* bkg_out, uint8_t* mask_out, tbk_ffi_status* status,
 	void* workspace, void* stream, float* ms);
 
+/* Diagnostics: out[i] = the device log10 used for the ring samples (table-driven, see tbk_common.cuh) of in[i];
+ * both device pointers.  Lets the tests bound its error against a host log10. */
+int tbk_debug_log10(const double* in, double* out, int n, void* stream);
+
 /* Number of kernels this library has launched in this process so far. */
 unsigned long long tbk_launch_count(void);
 

@@ -356,6 +356,12 @@ extern "C" int tbk_workspace_layout(const tbk_plan* p, int B, size_t* offsets, s
 	return TBK_OK;
 }
 
+extern "C" int tbk_debug_log10(const double* in, double* out, int n, void* stream)
+{
+	if (!in || !out || n <= 0) { tbk_set_error("tbk_debug_log10: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_log10(in, out, n, (cudaStream_t)stream);
+}
+
 extern "C" int tbk_decode_ffi_be(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W,
 	float* cube_out, void* stream)
 {

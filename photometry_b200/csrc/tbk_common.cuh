@@ -160,6 +160,38 @@ __device__ __forceinline__ void radial_stage(RadialSmem2& rs, const FfiCtl& c, c
 	}
 }
 
+#include "tbk_log10_table.cuh"
+
+// Table-driven float64 log10 for positive normal arguments (anything else takes the library path).
+// s = 2^k z with z in [0.6875, 1.375); the 7 leading mantissa bits of z pick 1/c and log10(c);
+// r = z/c - 1 (|r| < 2^-7, one fma) and log10(s) = k log10(2) + log10(c) + log1p(r)/ln(10).  The heads of
+// log10(2) and log10(c) carry 32 / 40 bits so their combination is exact; the degree-8 polynomial truncates below
+// 1e-20.  Error < 1 ulp (tests/test_gpu_parity.py::test_device_log10), at about a fifth of the instructions of log10().
+__device__ __forceinline__ double tbk_log10(double s, const double (*tab)[4])
+{
+	const int hi = __double2hiint(s);
+	if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log10(s);
+	const int t = hi - 0x3fe60000;
+	const int i = (t >> 13) & 127;
+	const double kd = (double)(t >> 20);
+	const double z = __hiloint2double(hi - (t & 0xfff00000), __double2loint(s));
+	const double2 e = *reinterpret_cast<const double2*>(tab[i]);   // 1/c, head
+	const double tail = tab[i][2];
+	const double r = fma(z, e.x, -1.0);
+	const double r2 = r * r;
+	const double a = fma(r, c_log10_poly[7], c_log10_poly[6]), b = fma(r, c_log10_poly[5], c_log10_poly[4]);
+	const double c = fma(r, c_log10_poly[3], c_log10_poly[2]), d = fma(r, c_log10_poly[1], c_log10_poly[0]);
+	const double p = fma(r2 * r2, fma(r2, a, b), fma(r2, c, d));
+	const double head = fma(kd, TBK_LOG10_2_HI, e.y);
+	return head + fma(r, p, fma(kd, TBK_LOG10_2_LO, tail));
+}
+
+// clamp without the NaN handling of fmin/fmax (v is finite)
+__device__ __forceinline__ double clamp_d(double v, double lo, double hi)
+{
+	return v < lo ? lo : (v > hi ? hi : v);
+}
+
 static __constant__ double c_exp_taylor[7] = {1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
 
 // 10**spline(clamp(r)) - zp.  Within a piece y = y_i + dy with |dy| small, so 10**y = 10**y_i * exp(ln10 dy):

@@ -603,55 +603,87 @@ __global__ void k_ring_gather(PlanDev P, Workspace ws, const float* __restrict__
 }
 
 // K_ring_gather_t: the same samples, pixels grouped by mesh: one CTA stages the mesh's 5x5 spline
-// coefficients and the weight table once and evaluates its ring pixels from shared memory.
+// coefficients, reduces them with the row weights once (R[row][B], see k_final) and evaluates its ring pixels
+// from shared memory with 4 DFMA each; log10 is the table-driven tbk_log10.
 __global__ void __launch_bounds__(256) k_ring_gather_t(PlanDev P, Workspace ws, const float* __restrict__ cube,
 	const uint8_t* __restrict__ mask, int round)
 {
 	__shared__ double sc[5][6];
 	__shared__ double wT[4][64];
+	__shared__ __align__(16) double R[2][64][4];
+	__shared__ __align__(16) double ltab[128][4];
 	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
 	const FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
 	const int tile = P.ringtile_id[slot];
 	const int ty = tile / P.nx, tx = tile % P.nx;
+	reinterpret_cast<double2*>(&ltab[0][0])[tid] = reinterpret_cast<const double2*>(&tbk_log10_tab[0][0])[tid];
 	if (round > 0) {
 		const double* coef = ws.coef + (size_t)b * P.ntiles;
 		if (tid < 25) sc[tid / 5][tid % 5] = coef[reflect_fold(ty - 2 + tid / 5, P.ny) * P.nx + reflect_fold(tx - 2 + tid % 5, P.nx)];
 		wT[tid & 3][tid >> 2] = __ldg(P.zoom_w + tid);
 		__syncthreads();
+		for (int e = tid; e < 64 * 5; e += 256) {
+			const int row = e & 63, B = e >> 6, oy = row >> 5;
+			double r = 0.0;
+#pragma unroll
+			for (int a = 0; a < 4; ++a) r = fma(wT[a][row], sc[oy + a][B], r);
+			if (B < 4) R[0][row][B] = r;
+			if (B > 0) R[1][row][B - 1] = r;
+		}
 	}
+	__syncthreads();
 	const double zp = c.zp, mmin = c.mesh_min, mmax = c.mesh_max;
 	const float zp32 = (float)c.zp;
-	const int mconst = c.mesh_const;
+	const bool mconst = c.mesh_const != 0;
 	const size_t img = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE;
 	double* __restrict__ dst = ws.ring_v + (size_t)b * P.nringpix;
 	const int lo = P.ringtile_ptr[slot], hi = P.ringtile_ptr[slot + 1];
-	for (int i = lo + tid; i < hi; i += 256) {
-		const unsigned ent = __ldg(P.ringtile_ent + i);
-		const int lr = (ent >> 6) & 63, lc = ent & 63;
-		const size_t off = img + (size_t)lr * P.W + lc;
-		double val = nan_d();
-		if (!__ldg(mask + off)) {
-			const float x = __ldg(cube + off);
-			if (round == 0) {
-				const float s = (x + 0.0f) + zp32;
-				val = (double)(float)log10((double)s);
-			} else {
-				const int oy = lr >> 5, ox = lc >> 5;
-				double acc = 0.0;
+	// four entries per thread and step: the entry, mask and pixel loads of a step are issued back to back (the
+	// kernel is bound by the latency of these dependent, scattered loads, not by arithmetic)
+	for (int i0 = lo + tid; i0 < hi; i0 += 4 * 256) {
+		unsigned ent[4]; uint8_t m[4]; float x[4];
 #pragma unroll
-				for (int a = 0; a < 4; ++a) {
-					double ra = 0.0;
+		for (int u = 0; u < 4; ++u) ent[u] = (i0 + 256 * u < hi) ? __ldg(P.ringtile_ent + i0 + 256 * u) : 0u;
 #pragma unroll
-					for (int q = 0; q < 4; ++q) ra += wT[q][lc] * sc[oy + a][ox + q];
-					acc += wT[a][lr] * ra;
-				}
-				const double sq = mconst ? mmin : fmin(fmax(acc, mmin), mmax);
-				val = log10(((double)x - sq) + zp);
-			}
+		for (int u = 0; u < 4; ++u) {
+			const size_t off = img + (size_t)((ent[u] >> 6) & 63) * P.W + (ent[u] & 63);
+			m[u] = __ldg(mask + off); x[u] = __ldg(cube + off);
 		}
-		dst[ent >> 12] = val;
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			if (i0 + 256 * u >= hi) break;
+			const int lr = (ent[u] >> 6) & 63, lc = ent[u] & 63;
+			double val = nan_d();
+			if (!m[u]) {
+				if (round == 0) {
+					const float s = (x[u] + 0.0f) + zp32;
+					val = (double)(float)tbk_log10((double)s, ltab);
+				} else {
+					const double2 ra = *reinterpret_cast<const double2*>(&R[lc >> 5][lr][0]);
+					const double2 rb = *reinterpret_cast<const double2*>(&R[lc >> 5][lr][2]);
+					const double acc = wT[0][lc] * ra.x + wT[1][lc] * ra.y + wT[2][lc] * rb.x + wT[3][lc] * rb.y;
+					const double sq = mconst ? mmin : clamp_d(acc, mmin, mmax);
+					val = tbk_log10(((double)x[u] - sq) + zp, ltab);
+				}
+			}
+			dst[ent[u] >> 12] = val;
+		}
 	}
+}
+
+__global__ void k_debug_log10(const double* __restrict__ in, double* __restrict__ out, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = tbk_log10(in[i], tbk_log10_tab);
+}
+
+int tbk_launch_log10(const double* in, double* out, int n, cudaStream_t st)
+{
+	k_debug_log10<<<(n + 255) / 256, 256, 0, st>>>(in, out, n);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_debug_log10: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1397,20 +1429,25 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 
 // ---------------------------------------------------------------------------------------------
 // K_final: bkg = img_bkg_radial + img_bkg_square (backgrounds.py:209), float32.
-// Mesh-uniform specialisations keep the per-pixel work at 8 DFMA + add + convert: the clip to
-// [mesh_min, mesh_max] is skipped when the 5x5 coefficient neighbourhood already lies inside that range
-// (a cubic B-spline value is a convex combination of its coefficients), and the radial term is a constant
-// for every mesh that cannot see beyond the first ring centre.
+// The zoom is separable: the row part  R[row][B] = sum_a wy[row][a] c[oy + a][B]  is the same for every pixel of a
+// mesh row, so it is computed once per mesh (64 x 5 values) and staged; a pixel then costs 4 DFMA + add + convert.
+// One CTA writes a strip of TBK_FINAL_NM horizontally adjacent meshes: the coefficient loads, the weight table and
+// the two barriers of the prologue are paid once per strip (the kernel is bound by that latency and by the store
+// stream, not by arithmetic).
+// Mesh-uniform specialisations: the clip to [mesh_min, mesh_max] is skipped when the 5x5 coefficient
+// neighbourhood already lies inside that range (a cubic B-spline value is a convex combination of its
+// coefficients), and the radial term is a constant for every mesh that cannot see beyond the first ring centre.
+#define TBK_FINAL_NM 4
 struct FinalSmem {
-	double c[5][6];          // coefficient neighbourhood, rows padded for 16-byte vector loads
-	double wT[4][64];        // zoom weights transposed: wT[tap][phase] (conflict-free per-lane loads)
-	double mesh_min, mesh_max, c_flat;
-	int mesh_const, radial_ok, need_clip;
+	double blk[5][TBK_FINAL_NM + 4];      // coefficient rows ty-2..ty+2, columns tx0-2..tx0+NM+1
+	double wT[4][64];                     // zoom weights transposed: wT[tap][phase] (conflict-free per-lane loads)
+	double R[TBK_FINAL_NM][2][64][4];     // row part for the left (coefficient columns 0..3) / right (1..4) mesh half
+	int need_clip[TBK_FINAL_NM];
 };
 
 template <bool CLIP, bool NONFLAT>
-__device__ __forceinline__ void final_rows(const FinalSmem& z, const RadialSmem2& rs, const PlanDev& P,
-	float* __restrict__ bkg, size_t img, int ty, int tx, int tid)
+__device__ __forceinline__ void final_rows(const FinalSmem& z, int m, const RadialSmem2& rs, const PlanDev& P,
+	double lo, double hi, double cflat, float* __restrict__ bkg, size_t img, int ty, int tx, int tid)
 {
 	const int lcol = tile_lcol(tid), ox = lcol >> 5;
 	const int gx = tx * TBK_TILE + lcol;
@@ -1421,18 +1458,13 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, const RadialSmem2
 		const double2 u1 = *reinterpret_cast<const double2*>(&z.wT[b][lcol + 2]);
 		wx[0][b] = u0.x; wx[1][b] = u0.y; wx[2][b] = u1.x; wx[3][b] = u1.y;
 	}
-	const double lo = z.mesh_min, hi = z.mesh_max, cflat = z.radial_ok ? z.c_flat : 0.0;
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
-		const int lrow = tile_lrow(tid, j), oy = lrow >> 5;
+		const int lrow = tile_lrow(tid, j);
 		const int gy = ty * TBK_TILE + lrow;
-		double r[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-		for (int a = 0; a < 4; ++a) {
-			const double wy = z.wT[a][lrow];
-#pragma unroll
-			for (int b = 0; b < 4; ++b) r[b] = fma(wy, z.c[oy + a][ox + b], r[b]);
-		}
+		const double2 ra = *reinterpret_cast<const double2*>(&z.R[m][ox][lrow][0]);
+		const double2 rb = *reinterpret_cast<const double2*>(&z.R[m][ox][lrow][2]);
+		const double r[4] = {ra.x, ra.y, rb.x, rb.y};
 		float o[4];
 		double rr[4] = {0.0, 0.0, 0.0, 0.0};
 		if (NONFLAT) {
@@ -1443,7 +1475,7 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, const RadialSmem2
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			double sq = wx[q][0] * r[0] + wx[q][1] * r[1] + wx[q][2] * r[2] + wx[q][3] * r[3];
-			if (CLIP) sq = fmin(fmax(sq, lo), hi);
+			if (CLIP) sq = clamp_d(sq, lo, hi);
 			const double rad = NONFLAT ? radial_value_s(rs, rr[q]) : cflat;
 			o[q] = (float)(rad + sq);
 		}
@@ -1454,52 +1486,74 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, const RadialSmem2
 __global__ void __launch_bounds__(TBK_NT, 4) k_final(PlanDev P, Workspace ws,
 	float* __restrict__ bkg, uint8_t* __restrict__ mask_out)
 {
-	__shared__ FinalSmem z;
+	__shared__ __align__(16) FinalSmem z;
 	__shared__ RadialSmem2 rs;
-	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const int nstrip = (P.nx + TBK_FINAL_NM - 1) / TBK_FINAL_NM;
+	const int ty = blockIdx.x / nstrip, tx0 = (blockIdx.x % nstrip) * TBK_FINAL_NM;
+	const int nm = min(TBK_FINAL_NM, P.nx - tx0);
+	const int b = blockIdx.y, tid = threadIdx.x;
 	const FfiCtl& c = ws.ctl[b];
-	const int ty = tile / P.nx, tx = tile % P.nx;
 	const size_t img = (size_t)b * P.H * P.W;
 	const int lcol = tile_lcol(tid);
-	const int gx = tx * TBK_TILE + lcol;
 	if (c.all_masked || c.no_good_mesh) {
 		const float q = nan_f();
+		for (int m = 0; m < nm; ++m) {
+			const int gx = (tx0 + m) * TBK_TILE + lcol;
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const size_t off = img + (size_t)(ty * TBK_TILE + tile_lrow(tid, j)) * P.W + gx;
-			*reinterpret_cast<float4*>(bkg + off) = make_float4(q, q, q, q);
-			if (c.all_masked) *reinterpret_cast<uchar4*>(mask_out + off) = make_uchar4(1, 1, 1, 1);
+			for (int j = 0; j < 4; ++j) {
+				const size_t off = img + (size_t)(ty * TBK_TILE + tile_lrow(tid, j)) * P.W + gx;
+				*reinterpret_cast<float4*>(bkg + off) = make_float4(q, q, q, q);
+				if (c.all_masked) *reinterpret_cast<uchar4*>(mask_out + off) = make_uchar4(1, 1, 1, 1);
+			}
 		}
 		return;
 	}
 	const double* coef = ws.coef + (size_t)b * P.ntiles;
-	if (tid < 25) {
-		const int a = tid / 5, bb = tid % 5;
-		z.c[a][bb] = coef[reflect_fold(ty - 2 + a, P.ny) * P.nx + reflect_fold(tx - 2 + bb, P.nx)];
+	if (tid < 5 * (TBK_FINAL_NM + 4)) {
+		const int a = tid / (TBK_FINAL_NM + 4), bb = tid % (TBK_FINAL_NM + 4);
+		z.blk[a][bb] = coef[reflect_fold(ty - 2 + a, P.ny) * P.nx + reflect_fold(tx0 - 2 + bb, P.nx)];
 	}
 	z.wT[tid & 3][tid >> 2] = __ldg(P.zoom_w + tid);
-	const bool nonflat = P.use_radial && c.radial_ok && P.tile_slot[tile] >= 0;
-	if (nonflat) radial_stage(rs, c, P);
+	const bool radial = P.use_radial && c.radial_ok;
+	bool any_nonflat = false;
+	if (radial) for (int m = 0; m < nm; ++m) any_nonflat |= P.tile_slot[ty * P.nx + tx0 + m] >= 0;
+	if (any_nonflat) radial_stage(rs, c, P);
+	const double mesh_min = c.mesh_min, mesh_max = c.mesh_max;
+	const int mesh_const = c.mesh_const;
+	const double cflat = c.radial_ok ? c.c_flat : 0.0;
 	__syncthreads();
-	if (tid < 32) {
-		double cmin = tid < 25 ? z.c[tid / 5][tid % 5] : INFINITY, cmax = tid < 25 ? z.c[tid / 5][tid % 5] : -INFINITY;
+	if (tid < 32 * TBK_FINAL_NM) {
+		// warp m decides whether mesh m needs the clip
+		const int m = tid >> 5, l = tid & 31;
+		const double v = l < 25 ? z.blk[l / 5][m + l % 5] : z.blk[0][m];
+		double cmin = v, cmax = v;
 		for (int o = 16; o > 0; o >>= 1) { cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); }
-		if (tid == 0) {
-		z.mesh_min = c.mesh_min; z.mesh_max = c.mesh_max; z.mesh_const = c.mesh_const;
-		z.radial_ok = c.radial_ok; z.c_flat = c.c_flat;
-		// small margin: the interpolated value can leave [cmin, cmax] only by rounding
-		const double eps = 1e-12 * fmax(fabs(cmin), fabs(cmax));
-		z.need_clip = !(cmin - eps >= c.mesh_min && cmax + eps <= c.mesh_max);
-		if (c.mesh_const) z.need_clip = 1;   // ptp(mesh) == 0: the clip returns the constant (BkgZoomInterpolator short-circuit)
+		if (l == 0) {
+			// small margin: the interpolated value can leave [cmin, cmax] only by rounding
+			const double eps = 1e-12 * fmax(fabs(cmin), fabs(cmax));
+			// ptp(mesh) == 0: the clip returns the constant (BkgZoomInterpolator short-circuit)
+			z.need_clip[m] = mesh_const || !(cmin - eps >= mesh_min && cmax + eps <= mesh_max);
 		}
 	}
+	for (int e = tid; e < nm * 64 * 5; e += TBK_NT) {
+		const int row = e & 63, B = (e >> 6) % 5, m = e / 320, oy = row >> 5;
+		double r = 0.0;
+#pragma unroll
+		for (int a = 0; a < 4; ++a) r = fma(z.wT[a][row], z.blk[oy + a][m + B], r);
+		if (B < 4) z.R[m][0][row][B] = r;
+		if (B > 0) z.R[m][1][row][B - 1] = r;
+	}
 	__syncthreads();
-	if (z.need_clip) {
-		if (nonflat) final_rows<true, true>(z, rs, P, bkg, img, ty, tx, tid);
-		else final_rows<true, false>(z, rs, P, bkg, img, ty, tx, tid);
-	} else {
-		if (nonflat) final_rows<false, true>(z, rs, P, bkg, img, ty, tx, tid);
-		else final_rows<false, false>(z, rs, P, bkg, img, ty, tx, tid);
+	for (int m = 0; m < nm; ++m) {
+		const int tx = tx0 + m;
+		const bool nonflat = radial && P.tile_slot[ty * P.nx + tx] >= 0;
+		if (z.need_clip[m]) {
+			if (nonflat) final_rows<true, true>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
+			else final_rows<true, false>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
+		} else {
+			if (nonflat) final_rows<false, true>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
+			else final_rows<false, false>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
+		}
 	}
 }
 
@@ -1570,7 +1624,7 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 		LAUNCH(TBK_K_MESH, (k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round)));
 		if (!launch_ok("round")) return TBK_ERR_CUDA;
 	}
-	LAUNCH(TBK_K_FINAL, (k_final<<<gt, TBK_NT, 0, st>>>(P, ws, bkg, mask)));
+	LAUNCH(TBK_K_FINAL, (k_final<<<dim3(P.ny * ((P.nx + TBK_FINAL_NM - 1) / TBK_FINAL_NM), B), TBK_NT, 0, st>>>(P, ws, bkg, mask)));
 	if (!launch_ok("final")) return TBK_ERR_CUDA;
 	if (prof) {
 		cudaError_t e = cudaStreamSynchronize(st);

@@ -23,4 +23,5 @@ int tbk_launch_sum_accumulate(const PlanDev& P, const float* cube, const float* 
 	double* sum, int32_t* nimg, int32_t* used, int* zero_flags, cudaStream_t st);
 int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg, const int32_t* used,
 	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, cudaStream_t st);
+int tbk_launch_log10(const double* in, double* out, int n, cudaStream_t st);
 int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W, float* out, cudaStream_t st);

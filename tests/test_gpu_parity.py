@@ -448,3 +448,40 @@ def test_load_ffi_stack_from_fits(tmp_path):
 	fit = pb.BackgroundFitter((2048, 2048), True, 2, 3)
 	bkg, mask, st = fit.fit(cube, pb.meta_from_headers(headers))
 	assert torch.isfinite(bkg).all() and int(mask[0, 5, 6]) == 1 and int(mask.sum()) == 3
+
+
+# ---- device math --------------------------------------------------------------------------------
+def test_device_log10():
+	"""
+	The ring samples use a table-driven float64 log10 (tbk_common.cuh:tbk_log10).  Bound its error against
+	numpy's log10 (itself < 1 ulp): at most 2 ulp apart anywhere on the range the path produces (pix + zp >= 1,
+	up to the flux cutoff scale) and on wide-range / special arguments, and exact at the powers of ten it can hit.
+	"""
+	import ctypes as C
+	from photometry_b200 import _lib
+	lib = _lib.load()
+	rng = np.random.default_rng(5)
+	x = np.concatenate([
+		1.0 + rng.uniform(0, 1e5, 400000),                 # the working range
+		np.exp(rng.uniform(np.log(0.5), np.log(2.0), 200000)),   # around 1 (every table interval)
+		np.exp(rng.uniform(-200, 200, 100000)),            # wide range
+		np.nextafter(2.0 ** np.arange(-20, 21), np.inf), np.nextafter(2.0 ** np.arange(-20, 21), 0),
+		10.0 ** np.arange(0, 16), [1.0, 0.6875, 1.375, np.nextafter(1.375, 0), 5e-324, 0.0, -1.0, np.inf, np.nan]])
+	xin = torch.from_numpy(x).cuda()
+	out = torch.empty_like(xin)
+	rc = lib.tbk_debug_log10(C.c_void_p(xin.data_ptr()), C.c_void_p(out.data_ptr()), x.size, None)
+	assert rc == 0
+	torch.cuda.synchronize()
+	got = out.cpu().numpy()
+	with np.errstate(all='ignore'):
+		ref = np.log10(x)
+	fin = np.isfinite(ref)
+	assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)])
+	ulp = np.spacing(np.abs(ref[fin]))
+	err = np.abs(got[fin] - ref[fin]) / ulp
+	near_zero = np.abs(ref[fin]) < 1e-3          # next to 1 the absolute error is what matters (|log10| -> 0)
+	assert err[~near_zero].max() <= 2.0, err[~near_zero].max()
+	assert np.abs(got[fin] - ref[fin])[near_zero].max() < 1e-18
+	p10 = 10.0 ** np.arange(0, 16)
+	sel = np.isin(x, p10)
+	assert np.abs(got[sel] - np.round(ref[sel])).max() <= 4.5e-16 * 15

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
 	__graft_entry__.build()
 	from photometry_b200 import _lib
 	hdr = open(os.path.join(ROOT, 'include', 'tbk.h')).read()
-	declared = set(re.findall(r'\b(tbk_[a-z_]+)\s*\(', hdr))
+	declared = set(re.findall(r'\b(tbk_[a-z0-9_]+)\s*\(', hdr))
 	assert {'tbk_plan_create', 'tbk_fit_batch', 'tbk_time_smooth', 'tbk_sum_accumulate', 'tbk_sum_finalize'} <= declared
 	lib = ctypes.CDLL(_lib.LIBPATH)
 	for name in declared:
