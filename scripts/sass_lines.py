@@ -12,6 +12,7 @@ ap.add_argument('sass'); ap.add_argument('kernel'); ap.add_argument('csv')
 ap.add_argument('--top', type=int, default=40)
 ap.add_argument('--depth', type=int, default=0, help='0 = outermost frame, 1 = one level below, ... -1 = innermost')
 ap.add_argument('--ops', action='store_true', help='aggregate by SASS opcode instead')
+ap.add_argument('--under', default=None, help='only instructions whose inline chain contains this file:line')
 ap.add_argument('--launch', type=int, default=0, help='which launch of the kernel in the csv')
 args = ap.parse_args()
 
@@ -56,6 +57,8 @@ for r in rows:
 	off = int(r[ia], 16) - base
 	ch, op = loc.get(off, (('?',), ''))
 	ch = ch or ('?',)
+	if args.under and args.under not in ch:
+		continue
 	key = ch[0] if args.depth < 0 else ch[max(len(ch) - 1 - args.depth, 0)]
 	if args.ops:
 		key = op.split()[1] if op.startswith('@') else op.split()[0]
