@@ -11,7 +11,8 @@ pass of ``fit_background`` over the whole device-resident 1,340-FFI cube (22.5 G
 Keys beyond the base contract: ``roofline`` (dominant kernel, CUDA-event timed), ``cpu_baseline``
 (the CPU oracle under the reference's spawn-Pool driver on this box's cores), ``kernel_ms`` (device
 time per kernel class for one step), ``prepare_path`` (fit + time smoothing + sumimage accumulation
-[+ NCCL reduce], FFIs/s).
+[+ NCCL reduce], FFIs/s), ``shenanigans_path`` (the background-shenanigans stage on the same frames, FFIs/s;
+algorithmic bytes per FFI = 2048^2 x 18: image read, indicator write + two re-reads, flags read + write).
 
 ``--impl reference`` times the reference's CPU path (restated oracle; the reference itself cannot be
 imported here) with all host cores on a bounded sample of the same workload.
@@ -290,7 +291,7 @@ def run_b200(args):
 	del host_in, host_bkg, host_mask
 
 	# ---- prepare path: fit + time smoothing + sumimage accumulation (+ NCCL reduce)
-	prep = None
+	prep = shen = None
 	if args.prepare:
 		np_ = min(n, args.prepare_ffis)
 		barrier()
@@ -308,7 +309,24 @@ def run_b200(args):
 			pms = float(t.item())
 		prep = {"value": world * np_ / (pms * 1e-3), "unit": "FFIs/s", "ffis_per_gpu": np_, "numfiles": res.numfiles,
 			"stages": "fit + time_smooth(w=1) + sum_accumulate + reduce + finalize"}
-		del res
+		# ---- background shenanigans (prepare.py:514-622) on the same frames: 15 x 15 median indicator per cadence,
+		# robust mean over shuffled blocks (cadence -> row-slab exchange when N > 1), flagging
+		flags_copy = res.pixel_flags.clone()
+		pb.background_shenanigans(res.images, res.sumimage, flags_copy)
+		barrier()
+		g0.record()
+		pb.background_shenanigans(res.images, res.sumimage, flags_copy)
+		g1.record()
+		barrier()
+		sms = g0.elapsed_time(g1)
+		if world > 1:
+			t = torch.tensor([sms], dtype=torch.float64, device=dev)
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+			sms = float(t.item())
+		shen = {"value": world * np_ / (sms * 1e-3), "unit": "FFIs/s", "ffis_per_gpu": np_,
+			"stages": "median-filter indicator + robust mean (blocks of 25) + flagging",
+			"algorithmic_bytes_per_ffi": 2048 * 2048 * 18, "hbm_frac": world * np_ / (sms * 1e-3) * 2048 * 2048 * 18 / (peak * 1e9 * world)}
+		del res, flags_copy
 
 	if rank != 0:
 		if world > 1:
@@ -339,6 +357,7 @@ def run_b200(args):
 			"ffis_per_step": ne, "note": "one e2e step = fit_stack_host over a pinned host stack; results (bkg f32 + mask u8) copied back to pinned host memory"},
 		"gpu_launches": launches, "clocks": clocks,
 		"kernel_ms": {k: round(v, 3) for k, v in prof.items()}, "prepare_path": prep,
+		"shenanigans_path": shen,
 	}
 	print(json.dumps(line), flush=True)
 	if world > 1:

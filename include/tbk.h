@@ -161,6 +161,25 @@ int tbk_fit_batch_profiled(tbk_plan* plan, const float* cube, int B, const tbk_f
 	const uint8_t* extra_mask, float* bkg_out, uint8_t* mask_out, tbk_ffi_status* status,
 	void* workspace, void* stream, float* ms);
 
+/*
+ * Background-shenanigans detection (photometry/pixel_flags.py:61-79, photometry/prepare.py:514-622).  All pointers
+ * are device pointers; no plan is needed.
+ *
+ * tbk_bkgshe_indicator: ind_out[k] = float32(median_filter(images[k] - sumimage, size=15, mode='reflect'))
+ *   (pixel_flags.py:74-77; the float32 cast is the dtype of ``pixel_flags_individual``, prepare.py:537).
+ *   sumimage may be NULL (SumImage=None).  Windows containing NaN give the median of their non-NaN values.
+ * tbk_bkgshe_mean: mean[p] = (1 / ceil(n / 25)) * sum over blocks of 25 cadences, taken in ``order`` (int32[n], the
+ *   shuffled indices of prepare.py:561-563), of nanmedian(block) with NaN -> 0 (prepare.py:556-576).  ``ind`` holds
+ *   n images of ``npix`` pixels, ``stride`` elements apart (so a slab of rows can be reduced on its own).
+ * tbk_bkgshe_flag: flags[k][p] = (flags[k][p] & ~bit) | (abs(ind[k][p] - mean[p]) > threshold ? bit : 0)
+ *   (prepare.py:603-612; bit = PixelQualityFlags.BackgroundShenanigans = 4).
+ */
+int tbk_bkgshe_indicator(const float* images, const double* sumimage, int B, int H, int W, float* ind_out, void* stream);
+int tbk_bkgshe_mean(const float* ind, size_t stride, size_t npix, int n, const int32_t* order, double* mean_out,
+	void* stream);
+int tbk_bkgshe_flag(const float* ind, const double* mean, int B, size_t npix, double threshold, int bit,
+	uint8_t* flags, void* stream);
+
 /* Diagnostics: out[i] = the device log10 used for the ring samples (table-driven, see tbk_common.cuh) of in[i];
  * both device pointers.  Lets the tests bound its error against a host log10. */
 int tbk_debug_log10(const double* in, double* out, int n, void* stream);

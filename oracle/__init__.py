@@ -22,3 +22,8 @@ from .prepare_oracle import (  # noqa: F401
 	time_smooth_backgrounds, sumimage_accumulate, prepare_stack,
 	TESS_DEFAULT_BITMASK, PIXEL_NOT_USED_FOR_BACKGROUND, PIXEL_MANUAL_EXCLUDE,
 )
+from . import shenanigans_oracle  # noqa: F401
+from .shenanigans_oracle import (  # noqa: F401
+	pixel_background_shenanigans, indicator_stack, nan_affected, shuffled_order, mean_shenanigans,
+	flag_shenanigans, background_shenanigans, PIXEL_BACKGROUND_SHENANIGANS,
+)

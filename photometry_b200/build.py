@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIBPATH = os.path.join(LIBDIR, 'libtbk.so')
-SOURCES = ['tbk_api.cu', 'tbk_fit.cu', 'tbk_prepare.cu']
+SOURCES = ['tbk_api.cu', 'tbk_fit.cu', 'tbk_prepare.cu', 'tbk_shenanigans.cu']
 NVCC_FLAGS = [
 	'-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
 	'-Xcompiler', '-fPIC', '-shared', '-diag-suppress', '177',

@@ -356,6 +356,25 @@ extern "C" int tbk_workspace_layout(const tbk_plan* p, int B, size_t* offsets, s
 	return TBK_OK;
 }
 
+extern "C" int tbk_bkgshe_indicator(const float* images, const double* sumimage, int B, int H, int W, float* ind_out, void* stream)
+{
+	if (!images || !ind_out || B <= 0 || H <= 0 || W <= 0 || B > 65535) { tbk_set_error("tbk_bkgshe_indicator: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_bkgshe_indicator(images, sumimage, B, H, W, ind_out, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_bkgshe_mean(const float* ind, size_t stride, size_t npix, int n, const int32_t* order, double* mean_out, void* stream)
+{
+	if (!ind || !order || !mean_out || n <= 0 || npix == 0 || stride < npix) { tbk_set_error("tbk_bkgshe_mean: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_bkgshe_mean(ind, stride, npix, n, order, mean_out, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_bkgshe_flag(const float* ind, const double* mean, int B, size_t npix, double threshold, int bit,
+	uint8_t* flags, void* stream)
+{
+	if (!ind || !mean || !flags || B <= 0 || B > 65535 || npix == 0 || bit <= 0 || bit > 255) { tbk_set_error("tbk_bkgshe_flag: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_bkgshe_flag(ind, mean, B, npix, threshold, bit, flags, (cudaStream_t)stream);
+}
+
 extern "C" int tbk_debug_log10(const double* in, double* out, int n, void* stream)
 {
 	if (!in || !out || n <= 0) { tbk_set_error("tbk_debug_log10: bad argument"); return TBK_ERR_INVALID; }

@@ -23,5 +23,8 @@ int tbk_launch_sum_accumulate(const PlanDev& P, const float* cube, const float* 
 	double* sum, int32_t* nimg, int32_t* used, int* zero_flags, cudaStream_t st);
 int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg, const int32_t* used,
 	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, cudaStream_t st);
+int tbk_launch_bkgshe_indicator(const float* images, const double* sum, int B, int H, int W, float* out, cudaStream_t st);
+int tbk_launch_bkgshe_mean(const float* ind, size_t stride, size_t npix, int n, const int* order, double* mean, cudaStream_t st);
+int tbk_launch_bkgshe_flag(const float* ind, const double* mean, int B, size_t npix, double threshold, int bit, uint8_t* flags, cudaStream_t st);
 int tbk_launch_log10(const double* in, double* out, int n, cudaStream_t st);
 int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W, float* out, cudaStream_t st);

@@ -91,6 +91,28 @@ CASES = {
 }
 
 
+def case_shenanigans():
+	"""
+	Background-shenanigans stage: 30 background-subtracted frames (one full block of 25 + a partial one, so the stale
+	slots of the reference's block buffer matter), a scattered-light blob in three cadences, a residual star field
+	(what the median filter is there to remove), NaN-free so every window is specified by the reference.
+	"""
+	rng = np.random.default_rng(77)
+	N, H, W = 30, 96, 112
+	imgs = rng.normal(0.0, 6.0, (N, H, W)).astype('float32')
+	stars = np.zeros((H, W), dtype='float32')
+	for _ in range(60):
+		stars[rng.integers(0, H), rng.integers(0, W)] += rng.uniform(50, 4000)
+	imgs += stars * rng.uniform(0.97, 1.03, (N, 1, 1)).astype('float32')
+	yy, xx = np.mgrid[0:H, 0:W]
+	for k, amp in ((4, 120.0), (5, 90.0), (17, -70.0)):
+		imgs[k] += (amp * np.exp(-(((yy - 30 - k) / 18.0) ** 2 + ((xx - 70 + k) / 25.0) ** 2))).astype('float32')
+	sumimage = (stars + rng.normal(0, 0.5, (H, W))).astype('float64')
+	flags = (rng.uniform(size=(N, H, W)) < 0.05).astype('uint8')          # NotUsedForBackground bits
+	flags[9] |= 4                                                          # a stale shenanigans flag that must be cleared
+	return dict(images=imgs, sumimage=sumimage, pixel_flags=flags)
+
+
 def load_golden(path):
 	"""Load a golden file and unpack the bit-packed masks."""
 	g = dict(np.load(path))

@@ -59,9 +59,25 @@ def run_case(name, case):
 	return out
 
 
+def run_shenanigans(case):
+	flags, mean, ind = oracle.background_shenanigans(case['images'], case['sumimage'], case['pixel_flags'])
+	return dict(images_sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(case['images']).tobytes()).digest(), dtype='uint8'),
+		shape=np.array(case['images'].shape), indicator=ind[[0, 4, 17, 29]], mean=mean,
+		flag_bits=np.packbits((flags & 4) != 0), flags_other=np.packbits((flags & 3) != 0), order=oracle.shuffled_order(case['images'].shape[0]))
+
+
 if __name__ == '__main__':
 	here = os.path.dirname(os.path.abspath(__file__))
+	only = sys.argv[1:]
+	if not only or 'shenanigans' in only:
+		from cases import case_shenanigans
+		res = run_shenanigans(case_shenanigans())
+		path = os.path.join(here, 'shenanigans.npz')
+		np.savez_compressed(path, **res)
+		print('shenanigans', {k: v.shape for k, v in res.items()}, '%.1f KiB' % (os.path.getsize(path) / 1024))
 	for name, fn in CASES.items():
+		if only and name not in only:
+			continue
 		res = run_case(name, fn())
 		path = os.path.join(here, name + '.npz')
 		np.savez_compressed(path, **res)
