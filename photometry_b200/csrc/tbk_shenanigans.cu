@@ -45,7 +45,9 @@ struct SheSmem {
 	uint32_t ring[SHE_K][SHE_CS];   // ring[row mod 15][c]: key of (row, c) for the 15 rows of the window
 	uint32_t kold[SHE_CS];          // key that left column c in the last slide ...
 	uint32_t knew[SHE_CS];          // ... and the key that replaced it (equal: column unchanged)
-	int nv[SHE_CS];                 // non-NaN keys of column c
+	int nv[SHE_CS];                 // non-NaN keys of column c (first row only)
+	uint32_t bd[SHE_K][SHE_W];      // per output column: the 15 keys next to its cut (selection scratch)
+	int nanflag[2];                 // a NaN key entered or left the window in the slide to an odd / even row
 };
 
 __device__ __forceinline__ uint32_t she_load_key(const float* __restrict__ img, const double* __restrict__ sum,
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(SHE_NT) k_bkgshe_median(const float* __restric
 	const float* img = images + img_off;
 	const int y1 = min(y0 + SHE_SEG, H);
 
+	if (tid < 2) sm.nanflag[tid] = 0;
 	// ---- window of the first row: rows y0-7 .. y0+7 of every column, sorted
 	int gx = 0;
 	if (tid < SHE_NC) {
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(SHE_NT) k_bkgshe_median(const float* __restric
 	__syncthreads();
 
 	const bool sel = tid < SHE_W && x0 + tid < W;
-	unsigned long long pp = 0ull;
+	uint32_t plo = 0u, phi = 0u;   // cut position per window column, 4 bits each: columns 0..7 / 8..14
 	int r = 0, m = 0;
 	uint32_t a = 0u;
 	if (sel) {
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(SHE_NT) k_bkgshe_median(const float* __restric
 		for (int j = 0; j < SHE_K; ++j) {
 			m += sm.nv[tid + j];
 			const int p = she_count_le(&sm.col[0][tid + j], a);
-			pp |= (unsigned long long)p << (4 * j);
+			if (j < 8) plo |= (uint32_t)p << (4 * j); else phi |= (uint32_t)p << (4 * (j - 8));
 			r += p;
 		}
 	}
@@ -148,64 +151,69 @@ __global__ void __launch_bounds__(SHE_NT) k_bkgshe_median(const float* __restric
 	for (int y = y0; y < y1; ++y) {
 		if (sel) {
 			float res = nan_f();
-			if (m == 0) { pp = 0ull; r = 0; }   // nothing but NaN: every key is above the cut
+			if (m == 0) { plo = phi = 0u; r = 0; }   // nothing but NaN: every key is above the cut
 			else {
+				// Walk the cut to t + 1 keys below it.  Down: the largest key below the cut moves above it; up: the
+				// smallest key above moves below.  Keys of lanes that walk up are complemented, so both directions take
+				// a maximum and the lanes of a warp share one loop.  bd[j][tid] = key of column j next to the cut on the
+				// side the walk eats from (0 = none).
 				const int t = (m - 1) >> 1;
-				uint32_t b = SHE_NANKEY;
-				if (r > t + 1) {
-					// walk down: move the largest key below the cut above it; the last one moved is the smallest above
-					uint32_t tl[SHE_K];
+				const bool dn = r >= t + 1;
+				const uint32_t flip = dn ? 0u : 0xFFFFFFFFu;
+				const int off = dn ? -1 : 0;
+				int steps = dn ? r - (t + 1) : (t + 1) - r;
+				const bool moved = steps > 0;
 #pragma unroll
-					for (int j = 0; j < SHE_K; ++j) {
-						const int p = (int)(pp >> (4 * j)) & 15;
-						tl[j] = p > 0 ? sm.col[p - 1][tid + j] : 0u;
-					}
-					do {
-						const uint32_t best = she_max15(tl);
-						const int arg = she_find15(tl, best);
-						pp -= 1ull << (4 * arg); --r;
-						b = best;
-						const int p = (int)(pp >> (4 * arg)) & 15;
-						const uint32_t nt = p > 0 ? sm.col[p - 1][tid + arg] : 0u;
+				for (int j = 0; j < SHE_K; ++j) {
+					const int pj = (int)((j < 8 ? plo >> (4 * j) : phi >> (4 * (j - 8))) & 15u);
+					const int idx = pj + off;
+					sm.bd[j][tid] = (idx >= 0 && idx < SHE_K) ? (sm.col[idx][tid + j] ^ flip) : 0u;
+				}
+				uint32_t last = 0u;
+				while (steps > 0) {
+					uint32_t v[SHE_K];
 #pragma unroll
-						for (int j = 0; j < SHE_K; ++j) tl[j] = (j == arg) ? nt : tl[j];
-					} while (r > t + 1);
-					a = she_max15(tl);
-				} else {
-					uint32_t hd[SHE_K];
+					for (int j = 0; j < SHE_K; ++j) v[j] = sm.bd[j][tid];
+					const uint32_t best = she_max15(v);
+					int arg = SHE_K - 1;
 #pragma unroll
-					for (int j = 0; j < SHE_K; ++j) {
-						const int p = (int)(pp >> (4 * j)) & 15;
-						hd[j] = p < SHE_K ? sm.col[p][tid + j] : SHE_NANKEY;
-					}
-					if (r < t + 1) {
-						// walk up: move the smallest key above the cut below it; the last one moved is the largest below
-						do {
-							const uint32_t best = she_min15(hd);
-							const int arg = she_find15(hd, best);
-							pp += 1ull << (4 * arg); ++r;
-							a = best;
-							const int p = (int)(pp >> (4 * arg)) & 15;
-							const uint32_t nh = p < SHE_K ? sm.col[p][tid + arg] : SHE_NANKEY;
+					for (int j = SHE_K - 2; j >= 0; --j) arg = (v[j] == best) ? j : arg;
+					const int sh = (arg & 7) << 2;
+					const uint32_t inc = dn ? (0u - (1u << sh)) : (1u << sh);   // -1 / +1 in the nibble (it stays within 0..15)
+					if (arg < 8) plo += inc; else phi += inc;
+					last = best;
+					const int pj = (int)(((arg < 8 ? plo : phi) >> sh) & 15u);
+					const int idx = pj + off;
+					sm.bd[arg][tid] = (idx >= 0 && idx < SHE_K) ? (sm.col[idx][tid + arg] ^ flip) : 0u;
+					--steps;
+				}
+				r = t + 1;
+				uint32_t v[SHE_K];
 #pragma unroll
-							for (int j = 0; j < SHE_K; ++j) hd[j] = (j == arg) ? nh : hd[j];
-						} while (r < t + 1);
-					} else {
-						a = 0u;
+				for (int j = 0; j < SHE_K; ++j) v[j] = sm.bd[j][tid];
+				const uint32_t top = she_max15(v);
+				a = dn ? top : ~last;                 // largest key below the cut
+				if (m & 1) res = she_val(a);
+				else {
+					uint32_t b;                       // smallest key above the cut
+					if (!dn) b = ~top;
+					else if (moved) b = last;
+					else {
+						b = SHE_NANKEY;
 #pragma unroll
 						for (int j = 0; j < SHE_K; ++j) {
-							const int p = (int)(pp >> (4 * j)) & 15;
-							if (p > 0) a = max(a, sm.col[p - 1][tid + j]);
+							const int pj = (int)((j < 8 ? plo >> (4 * j) : phi >> (4 * (j - 8))) & 15u);
+							if (pj < SHE_K) b = min(b, sm.col[pj][tid + j]);
 						}
 					}
-					b = she_min15(hd);
+					res = (float)(0.5 * ((double)she_val(a) + (double)she_val(b)));
 				}
-				res = (m & 1) ? she_val(a) : (float)(0.5 * ((double)she_val(a) + (double)she_val(b)));
 			}
 			out[img_off + (size_t)y * W + x0 + tid] = res;
 		}
 		if (y + 1 >= y1) break;
 		__syncthreads();
+		if (tid == SHE_NT - 1) sm.nanflag[y & 1] = 0;   // last read in the previous iteration's carry
 		if (tid < SHE_NC) {
 			// slide the window down: row y+8 replaces row y-7 in every column
 			const int rnew = y + 1 + SHE_R, slot = (rnew + 2 * SHE_K) % SHE_K;
@@ -213,6 +221,7 @@ __global__ void __launch_bounds__(SHE_NT) k_bkgshe_median(const float* __restric
 			const uint32_t knew = she_load_key(img, sum, H, W, rnew, gx);
 			sm.ring[slot][tid] = knew;
 			sm.kold[tid] = kold; sm.knew[tid] = knew;
+			if ((kold == SHE_NANKEY) != (knew == SHE_NANKEY)) sm.nanflag[(y + 1) & 1] = 1;
 			if (knew != kold) {
 				uint32_t c[SHE_K];
 				int pold = 0;
@@ -237,13 +246,17 @@ __global__ void __launch_bounds__(SHE_NT) k_bkgshe_median(const float* __restric
 			// carry the cut over to the new window: a key that left from below the cut takes one off, a key that
 			// arrived below it adds one; a key equal to the previous median may sit on either side, so that column is
 			// cut afresh (keys <= a below)
+			const bool nanrow = sm.nanflag[(y + 1) & 1] != 0;
 #pragma unroll
 			for (int j = 0; j < SHE_K; ++j) {
 				const uint32_t ko = sm.kold[tid + j], kn = sm.knew[tid + j];
-				m += (int)(kn != SHE_NANKEY) - (int)(ko != SHE_NANKEY);
+				if (nanrow) m += (int)(kn != SHE_NANKEY) - (int)(ko != SHE_NANKEY);
 				int d = (int)(kn < a) - (int)(ko < a);
-				if (ko != kn && (ko == a || kn == a)) d = she_count_le(&sm.col[0][tid + j], a) - ((int)(pp >> (4 * j)) & 15);
-				pp += (unsigned long long)(long long)d << (4 * j);
+				if (ko == a || kn == a) {
+					const int pj = (int)((j < 8 ? plo >> (4 * j) : phi >> (4 * (j - 8))) & 15u);
+					d = she_count_le(&sm.col[0][tid + j], a) - pj;
+				}
+				if (j < 8) plo += (uint32_t)d << (4 * j); else phi += (uint32_t)d << (4 * (j - 8));
 				r += d;
 			}
 		}

@@ -42,5 +42,32 @@ for ts in (3, 9):
 		assert torch.allclose(res.sumimage, sumimage, rtol=1e-12, equal_nan=True)
 		assert torch.equal(res.backgrounds_pixels_used, used)
 		print(f"time_smooth={ts}: {world}-rank sharded prepare_stack == single-GPU result (backgrounds bit-equal, sumimage rtol 1e-12)", flush=True)
+# ---- background shenanigans: cadence shards -> row slabs over NCCL must reproduce the single-GPU stage
+g = torch.Generator().manual_seed(11)
+n2, H2, W2 = 61, 130, 192
+imgs = torch.randn((n2, H2, W2), generator=g) * 6
+imgs[7, 30:80, 40:150] += 90
+imgs[40, 10:60, 100:190] -= 70
+imgs[3, 5, 5] = float('nan')
+sumimage = torch.randn((H2, W2), generator=g, dtype=torch.float64)
+flags0 = (torch.rand((n2, H2, W2), generator=g) < 0.1).to(torch.uint8) * 3
+lo, hi = shard_bounds(n2, world, rank)
+fl = flags0[lo:hi].clone().cuda()
+mean = pb.background_shenanigans(imgs[lo:hi].cuda(), sumimage.cuda() if rank == 0 else None, fl)
+torch.cuda.synchronize()
+parts = [None] * world
+dist.all_gather_object(parts, fl.cpu().numpy())
+means = [None] * world
+dist.all_gather_object(means, mean.cpu().numpy())
+if rank == 0:
+	# single-GPU reference through the non-distributed pieces
+	ind = pb.shenanigans_indicator(imgs.cuda(), sumimage.cuda())
+	m1 = pb.mean_shenanigans(ind)
+	f1 = flags0.clone().cuda()
+	pb.flag_shenanigans(ind, m1, f1)
+	assert all(np.array_equal(mm, m1.cpu().numpy()) for mm in means), "sharded mean_shenanigans differs"
+	assert np.array_equal(np.concatenate(parts), f1.cpu().numpy()), "sharded shenanigans flags differ"
+	print(f"background shenanigans: {world}-rank result == single-GPU result (mean image bit-equal on every rank, flags exact; "
+		f"{int((f1 & 4).bool().sum())} pixels flagged)", flush=True)
 dist.barrier()
 dist.destroy_process_group()
