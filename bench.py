@@ -251,7 +251,7 @@ def run_b200(args):
 		for kname, e in prof_json['kernels'].items():
 			if kname.split('<')[0].startswith('k_' + dom):
 				dom_traffic = (e['dram_read_bytes'] + e['dram_write_bytes']) / e['launches'] / prof_json['ffis_per_launch'] * min(chunk, n)
-	except (OSError, KeyError, ValueError):
+	except (OSError, KeyError, ValueError, AttributeError, TypeError, ZeroDivisionError):
 		pass
 	roofline = {"bound": "hbm", "kernel": "tbk_fit_batch (chain of 25 launches; sum of kernel device times)",
 		"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

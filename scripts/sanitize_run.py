@@ -11,4 +11,7 @@ n, H, W = imgs.shape
 fit = pb.BackgroundFitter((H, W), True, case['camera'], case['ccd'], xycen=case['xycen'], **case['fit_kwargs'])
 res = pb.prepare_stack(fit, torch.from_numpy(imgs).cuda(), pb.meta_from_headers(case['headers'][:4]), time_smooth=3, chunk=2)
 torch.cuda.synchronize()
-print('ok', float(res.sumimage.nanmean()))
+flags = res.pixel_flags.clone()
+mean = pb.background_shenanigans(res.images, res.sumimage, flags)
+torch.cuda.synchronize()
+print('ok', float(res.sumimage.nanmean()), float(mean.abs().max()))
