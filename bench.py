@@ -291,7 +291,7 @@ def run_b200(args):
 	del host_in, host_bkg, host_mask
 
 	# ---- prepare path: fit + time smoothing + sumimage accumulation (+ NCCL reduce)
-	prep = shen = None
+	prep = shen = stamps_path = None
 	if args.prepare:
 		np_ = min(n, args.prepare_ffis)
 		barrier()
@@ -326,7 +326,27 @@ def run_b200(args):
 		shen = {"value": world * np_ / (sms * 1e-3), "unit": "FFIs/s", "ffis_per_gpu": np_,
 			"stages": "median-filter indicator + robust mean (blocks of 25) + flagging",
 			"algorithmic_bytes_per_ffi": 2048 * 2048 * 18, "hbm_frac": world * np_ / (sms * 1e-3) * 2048 * 2048 * 18 / (peak * 1e9 * world)}
-		del res, flags_copy
+		# ---- consumer-side cube loads (BasePhotometry._load_cube): 2,000 stamps of 15 x 15 pixels over the frames
+		srv = pb.StampServer(images=res.images)
+		rs = np.random.default_rng(5)
+		r0 = rs.integers(0, H - 15, 2000); c0 = rs.integers(0, W - 15, 2000)
+		stamps_arr = np.stack([r0, r0 + 15, c0 + 44, c0 + 15 + 44], axis=1)
+		srv.load_cubes(stamps_arr, views=False)
+		barrier()
+		g0.record()
+		cubes = srv.load_cubes(stamps_arr, views=False)
+		g1.record()
+		barrier()
+		gms = g0.elapsed_time(g1)
+		if world > 1:
+			t = torch.tensor([gms], dtype=torch.float64, device=dev)
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+			gms = float(t.item())
+		moved = 2000 * 15 * 15 * np_ * 4 * 2
+		stamps_path = {"value": world * 2000 / (gms * 1e-3), "unit": "stamps/s", "stamps": 2000, "stamp": "15x15", "cadences": np_,
+			"achieved_gbs": moved / (gms * 1e-3) / 1e9, "hbm_frac": moved / (gms * 1e-3) / 1e9 / peak,
+			"note": "bytes = cube elements read + written; reads are 60-byte row segments (32-byte sectors)"}
+		del res, flags_copy, cubes, srv
 
 	if rank != 0:
 		if world > 1:
@@ -357,7 +377,7 @@ def run_b200(args):
 			"ffis_per_step": ne, "note": "one e2e step = fit_stack_host over a pinned host stack; results (bkg f32 + mask u8) copied back to pinned host memory"},
 		"gpu_launches": launches, "clocks": clocks,
 		"kernel_ms": {k: round(v, 3) for k, v in prof.items()}, "prepare_path": prep,
-		"shenanigans_path": shen,
+		"shenanigans_path": shen, "stamps_path": stamps_path,
 	}
 	print(json.dumps(line), flush=True)
 	if world > 1:

@@ -180,6 +180,16 @@ int tbk_bkgshe_mean(const float* ind, size_t stride, size_t npix, int n, const i
 int tbk_bkgshe_flag(const float* ind, const double* mean, int B, size_t npix, double threshold, int bit,
 	uint8_t* flags, void* stream);
 
+/*
+ * Consumer side (photometry/BasePhotometry.py:720-751, _load_cube): cut the stamps of S targets out of a device-resident
+ * stack [N, H, W] of 4-byte (images, images_err, backgrounds: float32) or 1-byte (pixel_flags) elements.
+ * stamps: int32 [S][4] = (row0, row1, col0, col1) in stack coordinates (the caller subtracts PIXEL_OFFSET_ROW / _COLUMN),
+ * half-open, inside the frame; out_offsets: int64 [S] element offsets into ``out``.  Stamp s is written as the
+ * C-ordered array [row1-row0][col1-col0][N] (rows, cols, times) the reference builds.  All pointers are device pointers.
+ */
+int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, const int32_t* stamps,
+	const int64_t* out_offsets, int S, void* out, void* stream);
+
 /* Diagnostics: out[i] = the device log10 used for the ring samples (table-driven, see tbk_common.cuh) of in[i];
  * both device pointers.  Lets the tests bound its error against a host log10. */
 int tbk_debug_log10(const double* in, double* out, int n, void* stream);

@@ -27,3 +27,4 @@ from .shenanigans_oracle import (  # noqa: F401
 	pixel_background_shenanigans, indicator_stack, nan_affected, shuffled_order, mean_shenanigans,
 	flag_shenanigans, background_shenanigans, PIXEL_BACKGROUND_SHENANIGANS,
 )
+from .cube_oracle import load_cube  # noqa: F401

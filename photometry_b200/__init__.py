@@ -12,3 +12,4 @@ from .ingest import load_ffi_stack, decode_ffi_be  # noqa: F401
 __version__ = '0.1.0'
 from .shenanigans import background_shenanigans, shenanigans_indicator, mean_shenanigans, flag_shenanigans  # noqa: F401
 from .pixel_flags import pixel_background_shenanigans  # noqa: F401
+from .stamps import StampServer  # noqa: F401

@@ -51,6 +51,7 @@ SIGNATURES = {
 	'tbk_bkgshe_indicator': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
 	'tbk_bkgshe_mean': (C.c_int, [_p, C.c_size_t, C.c_size_t, C.c_int, _p, _p, _p]),
 	'tbk_bkgshe_flag': (C.c_int, [_p, _p, C.c_int, C.c_size_t, C.c_double, C.c_int, _p, _p]),
+	'tbk_gather_stamps': (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, _p, _p]),
 	'tbk_debug_log10': (C.c_int, [_p, _p, C.c_int, _p]),
 	'tbk_decode_ffi_be': (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
 	'tbk_fit_batch_profiled': (C.c_int, [_p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.POINTER(C.c_float)]),

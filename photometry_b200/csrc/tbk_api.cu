@@ -375,6 +375,18 @@ extern "C" int tbk_bkgshe_flag(const float* ind, const double* mean, int B, size
 	return tbk_launch_bkgshe_flag(ind, mean, B, npix, threshold, bit, flags, (cudaStream_t)stream);
 }
 
+extern "C" int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, const int32_t* stamps,
+	const int64_t* out_offsets, int S, void* out, void* stream)
+{
+	if (!stack || !stamps || !out_offsets || !out || (elem_bytes != 1 && elem_bytes != 4) || N <= 0 || H <= 0 || W <= 0 || S <= 0 || S > 65535
+		|| ((uintptr_t)stamps & 15)) {
+		tbk_set_error("tbk_gather_stamps: bad argument"); return TBK_ERR_INVALID;
+	}
+	// enough CTAs per stamp to fill the device for a handful of stamps, few enough that thousands of stamps stay cheap
+	const int tiles_x = S >= 1184 ? 1 : (1184 + S - 1) / S;
+	return tbk_launch_gather_stamps(stack, elem_bytes, N, H, W, (const int*)stamps, (const long long*)out_offsets, S, tiles_x, out, (cudaStream_t)stream);
+}
+
 extern "C" int tbk_debug_log10(const double* in, double* out, int n, void* stream)
 {
 	if (!in || !out || n <= 0) { tbk_set_error("tbk_debug_log10: bad argument"); return TBK_ERR_INVALID; }

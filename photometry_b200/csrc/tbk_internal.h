@@ -26,5 +26,7 @@ int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg
 int tbk_launch_bkgshe_indicator(const float* images, const double* sum, int B, int H, int W, float* out, cudaStream_t st);
 int tbk_launch_bkgshe_mean(const float* ind, size_t stride, size_t npix, int n, const int* order, double* mean, cudaStream_t st);
 int tbk_launch_bkgshe_flag(const float* ind, const double* mean, int B, size_t npix, double threshold, int bit, uint8_t* flags, cudaStream_t st);
+int tbk_launch_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, const int* stamps,
+	const long long* offs, int S, int tiles_x, void* out, cudaStream_t st);
 int tbk_launch_log10(const double* in, double* out, int n, cudaStream_t st);
 int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W, float* out, cudaStream_t st);

@@ -191,3 +191,49 @@ int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row
 	if (e != cudaSuccess) { tbk_set_error("k_decode_ffi_be: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
 	return TBK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Stamp gather (consumer side, photometry/BasePhotometry.py:720-751 _load_cube): for a target's stamp
+// (rows r0..r1, columns c0..c1 of the CCD) build cube[r][c][k] = stack[k][r0 + r][c0 + c] -- the (rows, cols, times)
+// array every photometry method works on.  Reads run along the columns of a frame, writes along time, so 32 x 32
+// (time x column) tiles are transposed through shared memory.  Grid: x = tiles of a stamp (grid-stride), y = stamp.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_stamps(const T* __restrict__ stack, int N, int H, int W,
+	const int4* __restrict__ stamps, const long long* __restrict__ offs, T* __restrict__ out)
+{
+	__shared__ T tile[32][33];
+	const int4 st = stamps[blockIdx.y];   // r0, r1, c0, c1
+	const int h = st.y - st.x, w = st.w - st.z;
+	const int ntk = (N + 31) / 32, ntc = (w + 31) / 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	T* dst = out + offs[blockIdx.y];
+	for (int t = blockIdx.x; t < h * ntc * ntk; t += gridDim.x) {
+		const int r = t / (ntc * ntk), rem = t - r * (ntc * ntk);
+		const int cb = (rem / ntk) * 32, kb = (rem % ntk) * 32;
+#pragma unroll
+		for (int kk = ty; kk < 32; kk += 8) {
+			const int k = kb + kk, c = cb + tx;
+			if (k < N && c < w) tile[kk][tx] = __ldg(stack + ((size_t)k * H + st.x + r) * W + st.z + c);
+		}
+		__syncthreads();
+#pragma unroll
+		for (int cc = ty; cc < 32; cc += 8) {
+			const int c = cb + cc, k = kb + tx;
+			if (k < N && c < w) dst[((size_t)r * w + c) * N + k] = tile[tx][cc];
+		}
+		__syncthreads();
+	}
+}
+
+int tbk_launch_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, const int* stamps,
+	const long long* offs, int S, int tiles_x, void* out, cudaStream_t st)
+{
+	dim3 grid(tiles_x, S);
+	if (elem_bytes == 4)
+		k_gather_stamps<float><<<grid, 256, 0, st>>>((const float*)stack, N, H, W, (const int4*)stamps, offs, (float*)out);
+	else
+		k_gather_stamps<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)stack, N, H, W, (const int4*)stamps, offs, (uint8_t*)out);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_gather_stamps: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}
