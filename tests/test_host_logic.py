@@ -109,3 +109,27 @@ def test_product_path_fails_loudly_without_gpu():
 	from photometry_b200._lib import TbkError
 	with pytest.raises((TbkError, RuntimeError)):
 		pb.fit_background(np.full((128, 128), 1000, dtype='float32'))
+
+
+def test_abi_rejects_bad_arguments_without_touching_the_gpu():
+	"""Every entry point validates its arguments first and reports TBK_ERR_INVALID (-1) with a message: no CUDA call is made."""
+	import ctypes as C
+	from photometry_b200 import _lib
+	lib = _lib.load()
+	null = None
+	one = C.c_void_p(16)   # a non-null, aligned dummy; never dereferenced because another argument is invalid
+	plan = C.c_void_p()
+	assert lib.tbk_plan_create(C.byref(plan), 100, 64, 1, 1, 2, 8e4, 3, 2400.0, 15.0, 3, None, 0) == -1      # H not a multiple of 64
+	assert b'tbk_plan_create' in lib.tbk_last_error() or len(lib.tbk_last_error()) > 0
+	assert lib.tbk_plan_create(C.byref(plan), 2048, 2048, 1, 9, 9, 8e4, 3, 2400.0, 15.0, 3, None, 0) == -1    # unknown camera / ccd
+	assert lib.tbk_fit_batch(null, one, 1, one, null, one, one, one, one, null) == -1
+	assert lib.tbk_time_smooth(null, one, 1, 1, null, 0, null, 0, one, null) == -1
+	assert lib.tbk_bkgshe_indicator(null, null, 1, 64, 64, one, null) == -1
+	assert lib.tbk_bkgshe_indicator(one, null, 0, 64, 64, one, null) == -1
+	assert lib.tbk_bkgshe_mean(one, 10, 20, 3, one, one, null) == -1            # stride < npix
+	assert lib.tbk_bkgshe_flag(one, one, 1, 64, 40.0, 0, one, null) == -1       # bit out of range
+	assert lib.tbk_gather_stamps(one, 2, 4, 64, 64, one, one, 1, one, null) == -1   # element size must be 1 or 4
+	assert lib.tbk_decode_ffi_be(one, 1, 2136, 2078, 0, 44, 2048, 2050, one, null) == -1   # W % 4
+	assert lib.tbk_debug_log10(null, one, 4, null) == -1
+	assert lib.tbk_debug_fetch(null, one, 1, 0, 0, null, null) == -1
+	assert b'tbk_debug_fetch' in lib.tbk_last_error()
