@@ -150,3 +150,84 @@ def test_oracle_reproduces_golden(name, golden_dir):
 		b, m = oracle.fit_background(img, extra_mask=extra)
 	assert np.array_equal(m, g['mask'][k])
 	assert in_tolerance(b, g['bkg'][k]).all()
+
+
+# ---- further independent checks of the restated third-party pieces ------------------------------------
+def test_sextractor_rule_hand_cases():
+	"""photutils SExtractorBackground: 2.5 med - 1.5 mean; std == 0 -> mean; |mean - med| / std >= 0.3 -> med."""
+	nan = np.nan
+	rows = np.array([
+		[1.0, 2.0, 3.0, 4.0, 10.0, nan],      # med 3, mean 4, std 3.16: |1| / 3.16 = 0.316 >= 0.3 -> med
+		[1.0, 2.0, 3.0, 4.0, 5.5, nan],       # med 3, mean 3.1, std 1.56: 0.064 < 0.3 -> 2.5*3 - 1.5*3.1
+		[7.0, 7.0, 7.0, nan, nan, nan],       # std 0 -> mean
+	])
+	bkg, med, mean, std = oracle.sextractor_background(rows)
+	assert bkg[0] == 3.0 and med[0] == 3.0 and mean[0] == 4.0
+	np.testing.assert_allclose(bkg[1], 2.5 * 3.0 - 1.5 * 3.1, rtol=1e-15)
+	assert bkg[2] == 7.0 and std[2] == 0.0
+
+
+def test_mesh_exclusion_threshold_is_inclusive_at_half():
+	"""A mesh is kept iff its bad-pixel count (masked + clipped) is <= 50 % of 4096 (photutils exclude_percentile)."""
+	rng = np.random.default_rng(4)
+	data = (100 + rng.uniform(-1, 1, (64, 128))).astype('float64')   # uniform noise: 3 sigma never clips
+	mask = np.zeros((64, 128), dtype=bool)
+	mask.reshape(-1)[:0] = False
+	mask[:32, :64] = True                  # exactly 2048 bad pixels in mesh 0 -> kept
+	mask[:32, 64:] = True; mask[32, 64] = True   # 2049 in mesh 1 -> excluded, filled from mesh 0
+	b = oracle.Background2DOracle(data, mask, box=64)
+	assert b.mesh_good.tolist() == [[True, False]] and b.n_excluded == 1
+	assert b.mesh_unfiltered[0, 1] == b.mesh_unfiltered[0, 0]       # single neighbour -> its value
+
+
+def test_idw_tie_rules_agree_without_ties_and_differ_only_in_ties():
+	from oracle.backgrounds_oracle import _idw_fill
+	rng = np.random.default_rng(2)
+	# jittered positions: all distances distinct -> the traversal-independent rule must equal scipy's cKDTree
+	good = np.array([(iy, ix) for iy in range(6) for ix in range(7) if (iy, ix) not in [(2, 3), (2, 4), (3, 3)]], dtype='float64')
+	jit = good + rng.uniform(-0.2, 0.2, good.shape)
+	vals = rng.normal(100, 5, len(good))
+	a = _idw_fill(jit, vals, 6, 7, 'ckdtree'); b = _idw_fill(jit, vals, 6, 7, 'stable')
+	np.testing.assert_allclose(a, b, rtol=1e-14)
+	# on the integer lattice the two rules pick different members of an equidistant shell at most
+	a = _idw_fill(good, vals, 6, 7, 'ckdtree'); b = _idw_fill(good, vals, 6, 7, 'stable')
+	gy, gx = good[:, 0].astype(int), good[:, 1].astype(int)
+	np.testing.assert_array_equal(a[gy, gx], vals); np.testing.assert_array_equal(b[gy, gx], vals)   # good meshes keep their value
+	assert np.all(np.abs(a - b) < 5 * 5)   # same shells, different tie members: bounded by the spread of the values
+
+
+def test_zoom_restated_formula_matches_scipy():
+	"""BkgZoomInterpolator: scipy zoom(order=3, mode='reflect', grid_mode=True) + clip; the CUDA kernels use the closed
+	form u = (o + 0.5) / 64 - 0.5 with B-spline taps on prefiltered coefficients."""
+	from scipy import ndimage
+	rng = np.random.default_rng(6)
+	mesh = rng.normal(100, 5, (5, 7))
+	ref = ndimage.zoom(mesh, 64, order=3, mode='reflect', grid_mode=True)
+	coef = ndimage.spline_filter(mesh, order=3, mode='reflect')    # not grid_mode aware: 'reflect' == half-sample symmetric
+	def b3(t):
+		t = np.abs(t)
+		return np.where(t < 1, 2 / 3 - t * t + t ** 3 / 2, np.where(t < 2, (2 - t) ** 3 / 6, 0.0))
+	def fold(i, n):
+		i = np.where(i < 0, -i - 1, i)
+		return np.where(i >= n, 2 * n - 1 - i, i)
+	def axis_weights(n_out, n_in):
+		u = (np.arange(n_out) + 0.5) / 64 - 0.5
+		k0 = np.floor(u).astype(int) - 1
+		idx = np.stack([fold(k0 + a, n_in) for a in range(4)], axis=1)
+		w = np.stack([b3(u - (k0 + a)) for a in range(4)], axis=1)
+		return idx, w
+	iy, wy = axis_weights(5 * 64, 5); ix, wx = axis_weights(7 * 64, 7)
+	out = np.einsum('ya,xb,yaxb->yx', wy, wx, coef[iy[:, :, None, None], ix[None, None, :, :]])
+	np.testing.assert_allclose(out, ref, rtol=0, atol=2e-12)
+
+
+def test_not_a_knot_spline_equivalence():
+	"""InterpolatedUnivariateSpline(k=3) == not-a-knot cubic (what k_radial_fit solves); ext=3 clamps the abscissa."""
+	from scipy.interpolate import InterpolatedUnivariateSpline, CubicSpline
+	x = 2400 + 15 * np.arange(12) + 7.5
+	y = np.log10(150 + 0.002 * (x - 2400) ** 2)
+	s = InterpolatedUnivariateSpline(x, y, k=3, ext=3)
+	c = CubicSpline(x, y, bc_type='not-a-knot')
+	xx = np.linspace(x[0], x[-1], 500)
+	np.testing.assert_allclose(s(xx), c(xx), rtol=0, atol=1e-13)
+	assert s(x[0] - 100) == s(x[0]) and s(x[-1] + 100) == s(x[-1])
