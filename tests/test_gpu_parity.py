@@ -394,6 +394,23 @@ def test_more_parameter_variants(kw):
 	_compare_with_oracle(case['images'][1], case['headers'][1], xycen=case['xycen'], **kw2)
 
 
+@pytest.mark.parametrize('step', [45, 60])
+def test_wide_rings_take_the_unstaged_kde_path(step):
+	"""
+	Rings of more than 16,384 pixels do not fit the 16-bit bin staging of k_ring_kde and go through the sweep that
+	recomputes the bins (radial_pixel_step = 45 at full size: up to 57 k pixels per ring); with step 60 the first
+	rings exceed 65,535 samples and the linear binning switches from the fixed-point counters to float64 adds.
+	Small rings elsewhere in this file cover the staged / fixed-point paths.
+	"""
+	from photometry_b200 import synth
+	img = synth.synth_stack_numpy(1, 2048, 2048, camera=1, ccd=2, seed=314)[0]
+	hdr = header(1, 2, 0)
+	fit = pb.BackgroundFitter((2048, 2048), True, 1, 2, radial_pixel_step=step)
+	assert fit.nrings < 20
+	st, d = _compare_with_oracle(img, hdr, radial_pixel_step=step)
+	assert st['rounds'] == 3 and (st['radial_ok'][:3] == 1).all()
+
+
 @pytest.mark.parametrize('seed', list(range(40, 48)))
 def test_randomised_fields(seed):
 	"""Random backgrounds / star densities / NaN and mask fractions, TESS and non-TESS, against the live oracle."""
