@@ -121,13 +121,16 @@ def main():
 	ap.add_argument('--out', default=None)
 	ap.add_argument('--n', type=int, default=16)
 	ap.add_argument('--procs', type=int, default=min(os.cpu_count() or 1, 16))
+	ap.add_argument('--seed-offset', type=int, default=0, help='added to the survey seeds (a second, independent sample)')
 	args = ap.parse_args()
 	lines = []
 
 	def log(s):
 		print(s, flush=True); lines.append(s)
 	import torch
-	log(f"Parity report, GPU path vs oracle (idw='stable'), {torch.cuda.get_device_name(0)}")
+	log(f"Parity report, GPU path vs oracle (idw='stable'), {torch.cuda.get_device_name(0)}, seed offset {args.seed_offset}")
+	global BASE_SEED
+	BASE_SEED += args.seed_offset
 	with mp.get_context('spawn').Pool(args.procs) as pool:
 		# config 1: the reference's CPU-runnable case substituted by synthetic camera 1 / CCD 4, cadences 4697-4700 (Mars exclude)
 		run_config('config 1 (mars)', pool, 1, 4, 4, 4697, BASE_SEED + 0, {}, log=log)
