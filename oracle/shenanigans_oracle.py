@@ -89,7 +89,14 @@ def mean_shenanigans(ind, block=BKGSHE_BLOCK):
 
 
 def flag_shenanigans(ind, mean, pixel_flags, threshold=BKGSHE_THRESHOLD):
-	"""prepare.py:581-612: clear the old bit, set it where ``abs(indicator - mean) > threshold``; uint8 flags."""
+	"""
+	prepare.py:581-612: clear the old bit, set it where ``abs(indicator - mean) > threshold``; uint8 flags.
+
+	The reference's clearing step reads ``indx = (flags & PixelQualityFlags.BackgroundShenanigans != 0)`` (prepare.py:606),
+	which Python parses as ``flags & (FLAG != 0)`` = ``flags & 1``; its stated intent ("Clear any old flags") is what is
+	restated here.  On a first run no pixel carries the bit yet, so the two readings only differ when the stage is
+	re-run over an already flagged file.
+	"""
 	ind = np.asarray(ind)
 	flags = np.array(pixel_flags, dtype='uint8', copy=True)
 	for k in range(ind.shape[0]):

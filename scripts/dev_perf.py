@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import photometry_b200 as pb
 from photometry_b200 import synth
-n = 256
+n = 512
 dev = torch.device('cuda:0')
 cube = synth.synth_stack_torch(n, 2048, 2048, dev, camera=1, ccd=2, seed=20260118)
 hdrs = [dict(CAMERA=1, CCD=2, TSTART=1400.0 + k * 0.0208, TSTOP=1400.0208 + k * 0.0208, FFIINDEX=9000 + k) for k in range(n)]
@@ -24,7 +24,7 @@ for chunk in [int(a) for a in sys.argv[1:]] or [16, 64]:
 	print(f"chunk={chunk}: {n / ms * 1e3:.0f} FFIs/s ({ms / n * 1e3:.1f} us/FFI)  per-FFI us: " + ' '.join(f"{k}={v / n * 1e3:.1f}" for k, v in prof.items()), flush=True)
 
 
-for ns, chunk in ((2, 32), (2, 64), (3, 32), (4, 16)):
+for ns, chunk in ((2, 32), (2, 64), (3, 32), (4, 16), (2, 96), (2, 128), (3, 64), (4, 64)):
 	for rep in range(2):
 		torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True); e0.record()
 		fit.fit_stack(cube, meta, bk, mk, chunk=chunk, nstreams=ns)
