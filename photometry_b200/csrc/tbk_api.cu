@@ -31,8 +31,8 @@ struct tbk_plan {
 	std::vector<void*> allocs;
 	int* zero_flags;
 	int zero_cap;
-	int tile_kernel;   // TBK_TILE_KERNEL: 0 = generic CTA-per-mesh kernels, 1 = one warp per mesh (registers), 2 = two warps per mesh (registers), 3 = two warps per mesh, keys staged in shared memory (default)
-	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow;
+	int tile_kernel;   // TBK_TILE_KERNEL: 0 = generic CTA-per-mesh kernels, 1 = one warp per mesh (registers), 2 = two warps per mesh (registers), 3 = two warps per mesh, keys staged in shared memory (default), 5 = zone-limited buffer, mesh streamed twice from L2
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb;
 };
 
 // photometry/backgrounds.py:121-138
@@ -89,6 +89,7 @@ static void layout(tbk_plan* p, int B, size_t* total)
 	p->off_ringv = o;  o = align_up(o + sizeof(double) * (size_t)B * std::max(P.nringpix, 1));
 	p->off_sbmin = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
 	p->off_sblow = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
+	p->off_fb = o;     o = align_up(o + 256 + sizeof(int) * (size_t)B * P.ntiles);
 	*total = o;
 }
 
@@ -108,6 +109,8 @@ static Workspace carve(tbk_plan* p, void* base, int B)
 	ws.ring_v = (double*)(b + p->off_ringv);
 	ws.sbmin = (float*)(b + p->off_sbmin);
 	ws.sblow = (float*)(b + p->off_sblow);
+	ws.fb_count = (int*)(b + p->off_fb);
+	ws.fb_list = (int*)(b + p->off_fb + 256);
 	return ws;
 }
 
@@ -137,7 +140,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
 	p->zero_flags = nullptr; p->zero_cap = 0;
-	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel < 0 || p->tile_kernel > 4) p->tile_kernel = 3; }
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel < 0 || p->tile_kernel > 5) p->tile_kernel = 3; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;

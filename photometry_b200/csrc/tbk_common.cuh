@@ -82,6 +82,8 @@ struct Workspace {
 	double* ring_v;         // [B][nringpix] ring samples (NaN = masked)
 	float* sbmin;           // [B][ntiles][64] minimum valid pixel of every 8x8 sub-block (+inf = none)
 	float* sblow;           // [B][ntiles][64] lower bound of min(x - sq) per sub-block (zeropoint pruning)
+	int* fb_count;          // [1] meshes queued for the full-buffer statistics (TBK_TILE_KERNEL=5)
+	int* fb_list;           // [B * ntiles] queue entries b * ntiles + tile
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -160,8 +160,8 @@ __device__ __forceinline__ K warp_bitonic32(K v, int lane)
 }
 
 // keys at sorted ranks q and q+1 (when want2) among the span [s, e) of one bin (unsorted inside).
-template <typename T>
-__device__ __noinline__ void tw_select_in_span(const typename T::K* keys, uint32_t s, uint32_t e, uint32_t q, bool want2,
+template <typename T, typename Keys>
+__device__ __noinline__ void tw_select_in_span(const Keys& keys, uint32_t s, uint32_t e, uint32_t q, bool want2,
 	int lane, typename T::K& k1, typename T::K& k2)
 {
 	typedef typename T::K K;
@@ -190,19 +190,19 @@ __device__ __noinline__ void tw_select_in_span(const typename T::K* keys, uint32
 }
 
 // median (mean of the values at sorted ranks P and P+1 when ``even``) by bin lookup
-template <typename T>
-__device__ __forceinline__ double tw_median_at(const typename T::K* keys, const uint32_t* cnt, uint32_t P, bool even, int lane)
+template <typename T, typename Keys>
+__device__ __forceinline__ double tw_median_at(const Keys& keys, const uint32_t* cnt, uint32_t P, bool even, int lane)
 {
 	typedef typename T::K K;
 	const int b = tw_find_bin(cnt, P, lane);
 	const uint32_t bs = tw_cstart(cnt, b), be = tw_cend(cnt, b);
 	K k1, k2;
 	const bool second_here = even && (P + 1u < be);
-	tw_select_in_span<T>(keys, bs, be, P - bs, second_here, lane, k1, k2);
+	tw_select_in_span<T, Keys>(keys, bs, be, P - bs, second_here, lane, k1, k2);
 	if (even && !second_here) {
 		const int b2 = tw_find_bin(cnt, P + 1u, lane);
 		K dummy;
-		tw_select_in_span<T>(keys, tw_cstart(cnt, b2), tw_cend(cnt, b2), 0u, false, lane, k2, dummy);
+		tw_select_in_span<T, Keys>(keys, tw_cstart(cnt, b2), tw_cend(cnt, b2), 0u, false, lane, k2, dummy);
 	}
 	return 0.5 * (T::val(k1) + T::val(k2));
 }
@@ -235,8 +235,8 @@ __device__ __forceinline__ void tw_scan_counts(uint32_t* cnt, int lane)
 
 // The clip iterations + final statistics on bucketed keys (one warp).  Inputs: the moments about
 // ``pivot`` of the core bins [t0e, t1s) (s1c, s2c) and of the two overflow bins (tn, t1, t2).
-template <typename T>
-__device__ TileStat tw_iterate(const typename T::K* keys, const uint32_t* cnt, const typename T::Map& bm,
+template <typename T, typename Keys>
+__device__ TileStat tw_iterate(const Keys& keys, const uint32_t* cnt, const typename T::Map& bm,
 	int nvalid, double pivot, double s1c, double s2c, int tn, double t1, double t2, int lane)
 {
 	typedef typename T::K K;
@@ -263,7 +263,7 @@ __device__ TileStat tw_iterate(const typename T::K* keys, const uint32_t* cnt, c
 		const double m1 = (s1c + t1) / (double)n;
 		mean = pivot + m1;
 		sd = sqrt(fmax((s2c + t2) / (double)n - m1 * m1, 0.0));
-		med = tw_median_at<T>(keys, cnt, below + (uint32_t)((n - 1) >> 1), (n & 1) == 0, lane);
+		med = tw_median_at<T, Keys>(keys, cnt, below + (uint32_t)((n - 1) >> 1), (n & 1) == 0, lane);
 		if (it == 5) { exhausted = true; break; }   // five bound computations done: buffer after the last clip
 		lo_last = T::key_ceil(med - 3.0 * sd);
 		hi_last_ok = T::key_floor(med + 3.0 * sd, hi_last);
@@ -328,7 +328,7 @@ __device__ TileStat tw_iterate(const typename T::K* keys, const uint32_t* cnt, c
 		const double m1 = f1 / (double)fn;
 		out.mean = pivot + m1;
 		out.std = sqrt(fmax(f2 / (double)fn - m1 * m1, 0.0));
-		out.med = tw_median_at<T>(keys, cnt, s + (uint32_t)nb + (uint32_t)((fn - 1) >> 1), (fn & 1) == 0, lane);
+		out.med = tw_median_at<T, Keys>(keys, cnt, s + (uint32_t)nb + (uint32_t)((fn - 1) >> 1), (fn & 1) == 0, lane);
 	}
 	return out;
 }
