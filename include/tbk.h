@@ -194,6 +194,17 @@ int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, co
  * both device pointers.  Lets the tests bound its error against a host log10. */
 int tbk_debug_log10(const double* in, double* out, int n, void* stream);
 
+/*
+ * Diagnostics, HOST execution, host pointers: the 10 nearest good meshes of every mesh position exactly as the IDW fill of
+ * tbk_fit_batch chooses them -- the restatement of scipy.spatial.cKDTree(yx_good, leafsize=10).query(k=10) that photutils'
+ * ShepardIDWInterpolator runs (photometry/backgrounds.py:200-205), tie order included.  good: uint8 [ny*nx], non-zero = good
+ * mesh.  Outputs (any may be NULL): nbr_id / nbr_d2 int32 [ny*nx][10] (mesh id, squared distance; -1 past the number of good
+ * meshes), idx_out int32 [ngood] (the tree's index permutation, cKDTree.indices), nodes_out int32 [<= 2 ngood + 2][4] =
+ * (split_dim or -1, split, lesser | start, greater | end), nnodes_out int32 [1].  Lets the CPU tests compare with the real scipy.
+ */
+int tbk_debug_idw_neighbors(const uint8_t* good, int ny, int nx, int32_t* nbr_id, int32_t* nbr_d2,
+	int32_t* idx_out, int32_t* nodes_out, int32_t* nnodes_out);
+
 /* Number of kernels this library has launched in this process so far. */
 unsigned long long tbk_launch_count(void);
 

@@ -228,22 +228,29 @@ def sextractor_background(rows):
 	return bkg, med, mean, std
 
 
+# photutils 1.3.0 ``ShepardIDWInterpolator.__init__(coordinates, values, weights=None, leafsize=10)`` builds
+# ``cKDTree(coordinates, leafsize=leafsize)``; Background2D does not override it.  (scipy's own default is 16, which
+# gives different leaves and therefore different tie decisions on the mesh lattice -- pinned by tests/test_kdtree.py.)
+PHOTUTILS_IDW_LEAFSIZE = 10
+
+
 def _idw_fill(good_yx, good_values, ny, nx, mode):
 	"""
 	photutils 1.3.0 ``Background2D._interpolate_meshes``: ShepardIDWInterpolator over the good
 	meshes evaluated at every mesh position, n_neighbors=10, power=1, reg=0, conf_dist=1e-12.
 
-	mode='ckdtree': neighbours exactly as ``scipy.spatial.cKDTree.query(k=10)`` returns them
-	                (the reference; ties between equidistant lattice points are resolved by the
-	                tree traversal order).
-	mode='stable' : neighbours are the 10 smallest by (squared distance, good-mesh order), a
-	                traversal-independent rule; this is what the CUDA path implements.
+	mode='ckdtree': neighbours exactly as ``scipy.spatial.cKDTree(yx, leafsize=10).query(k=10)`` returns them
+	                (the reference; ties between equidistant lattice points are resolved by the tree's leaf
+	                order and traversal order).  This is the default and what the CUDA path reproduces.
+	mode='stable' : neighbours are the 10 smallest by (squared distance, good-mesh order) -- the rule the
+	                round-1 CUDA path used; kept only to quantify how far that rule was from the reference
+	                (tests/test_kdtree.py::test_stable_rule_deviation).
 	"""
 	coords = np.array([(iy, ix) for iy in range(ny) for ix in range(nx)], dtype='float64')
 	k = 10
 	npts = good_yx.shape[0]
 	if mode == 'ckdtree':
-		dist, idx = cKDTree(good_yx).query(coords, k=k, eps=0.0)
+		dist, idx = cKDTree(good_yx, leafsize=PHOTUTILS_IDW_LEAFSIZE).query(coords, k=k, eps=0.0)
 	elif mode == 'stable':
 		d2 = ((coords[:, None, :] - good_yx[None, :, :]) ** 2).sum(axis=2)
 		kk = min(k, npts)
@@ -267,8 +274,9 @@ def _idw_fill(good_yx, good_values, ny, nx, mode):
 		if np.any(confused):
 			out[p] = good_values[idk[confused][0]]
 			continue
-		w = 1.0 / dk
-		out[p] = np.dot(w, good_values[idk]) / np.sum(w)
+		w = 1.0 / ((dk ** 1.0) + 0.0)
+		wsum = np.sum(w)
+		out[p] = np.sum(w * good_values[idk]) / wsum
 	return out.reshape(ny, nx)
 
 
@@ -278,7 +286,7 @@ class Background2DOracle:
 	bkg_estimator=SExtractorBackground, mask=mask, exclude_percentile=50)`` as called at
 	photometry/backgrounds.py:200-205.  ``.background`` is the float64 full-resolution map.
 	"""
-	def __init__(self, data, mask, box=64, exclude_percentile=50.0, idw='stable'):
+	def __init__(self, data, mask, box=64, exclude_percentile=50.0, idw='ckdtree'):
 		data = np.asarray(data)
 		H, W = data.shape
 		if H % box or W % box:
@@ -368,7 +376,7 @@ def _ring_statistic(rvals, values, bins, discarded_bins):
 
 
 def fit_background(image, catalog=None, flux_cutoff=8e4, bkgiters=3, radial_cutoff=2400,
-	radial_pixel_step=15, radial_smooth=3, *, extra_mask=None, xycen=None, idw='stable',
+	radial_pixel_step=15, radial_smooth=3, *, extra_mask=None, xycen=None, idw='ckdtree',
 	discarded_bins=False, diagnostics=None):
 	"""
 	photometry/backgrounds.py:52-211.  ``image`` is a 2-D ndarray (non-TESS path) or an
@@ -376,8 +384,8 @@ def fit_background(image, catalog=None, flux_cutoff=8e4, bkgiters=3, radial_cuto
 
 	Extensions beyond the reference (all default-off): ``extra_mask`` is OR-ed into the mask at
 	the point of backgrounds.py:90 (star-mask extension); ``xycen`` overrides
-	the camera-centre table so the radial path can be exercised on small images; ``idw`` picks
-	the neighbour tie rule (see ``_idw_fill``); ``diagnostics`` (dict) receives intermediates.
+	the camera-centre table so the radial path can be exercised on small images; ``idw='stable'``
+	switches to the round-1 neighbour rule for comparison (see ``_idw_fill``); ``diagnostics`` (dict) receives intermediates.
 	"""
 	img0 = image if isinstance(image, FFIImageLite) else FFIImageLite(image)
 	if img0.data.ndim != 2:

@@ -92,10 +92,10 @@ def flag_shenanigans(ind, mean, pixel_flags, threshold=BKGSHE_THRESHOLD):
 	"""
 	prepare.py:581-612: clear the old bit, set it where ``abs(indicator - mean) > threshold``; uint8 flags.
 
-	The reference's clearing step reads ``indx = (flags & PixelQualityFlags.BackgroundShenanigans != 0)`` (prepare.py:606),
-	which Python parses as ``flags & (FLAG != 0)`` = ``flags & 1``; its stated intent ("Clear any old flags") is what is
-	restated here.  On a first run no pixel carries the bit yet, so the two readings only differ when the stage is
-	re-run over an already flagged file.
+	The reference's clearing step reads ``indx = (flags & PixelQualityFlags.BackgroundShenanigans != 0)`` (prepare.py:606).
+	In Python ``&`` binds tighter than ``!=``, so this is ``(flags & 4) != 0``: exactly the pixels that carry the old bit,
+	from which the bit is then subtracted (``np.array([0, 1, 4, 5, 2]) & 4 != 0 -> [F, F, T, T, F]``).  That is what is
+	restated here (clear the bit, then set it where the indicator pops out).
 	"""
 	ind = np.asarray(ind)
 	flags = np.array(pixel_flags, dtype='uint8', copy=True)

@@ -57,6 +57,7 @@ SIGNATURES = {
 	'tbk_fit_batch_profiled': (C.c_int, [_p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.POINTER(C.c_float)]),
 	'tbk_launch_count': (C.c_ulonglong, []),
 	'tbk_workspace_layout': (C.c_int, [_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+	'tbk_debug_idw_neighbors': (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
 	'tbk_last_error': (C.c_char_p, []),
 	'tbk_version': (C.c_int, []),
 }

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include "tbk_common.cuh"
 #include "tbk_internal.h"
+#include "tbk_kdtree.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -31,8 +32,8 @@ struct tbk_plan {
 	std::vector<void*> allocs;
 	int* zero_flags;
 	int zero_cap;
-	int tile_kernel;   // TBK_TILE_KERNEL: 0 = generic CTA-per-mesh kernels, 1 = one warp per mesh (registers), 2 = two warps per mesh (registers), 3 = two warps per mesh, keys staged in shared memory (default), 5 = zone-limited buffer, mesh streamed twice from L2
-	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb;
+	int tile_kernel;   // TBK_TILE_KERNEL (development / cross-check switch): 0 = generic CTA-per-mesh kernels, 3 = bucketed kernels (default)
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb, off_idwbits, off_idwtab;
 };
 
 // photometry/backgrounds.py:121-138
@@ -90,6 +91,8 @@ static void layout(tbk_plan* p, int B, size_t* total)
 	p->off_sbmin = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
 	p->off_sblow = o;  o = align_up(o + sizeof(float) * (size_t)B * P.ntiles * 64);
 	p->off_fb = o;     o = align_up(o + 256 + sizeof(int) * (size_t)B * P.ntiles);
+	p->off_idwbits = o; o = align_up(o + sizeof(uint32_t) * (size_t)B * ((P.ntiles + 31) / 32 + 1));
+	p->off_idwtab = o; o = align_up(o + sizeof(uint16_t) * (size_t)B * P.ntiles * 10);
 	*total = o;
 }
 
@@ -111,6 +114,8 @@ static Workspace carve(tbk_plan* p, void* base, int B)
 	ws.sblow = (float*)(b + p->off_sblow);
 	ws.fb_count = (int*)(b + p->off_fb);
 	ws.fb_list = (int*)(b + p->off_fb + 256);
+	ws.idw_bits = (uint32_t*)(b + p->off_idwbits);
+	ws.idw_tab = (uint16_t*)(b + p->off_idwtab);
 	return ws;
 }
 
@@ -140,7 +145,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
 	p->zero_flags = nullptr; p->zero_cap = 0;
-	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel < 0 || p->tile_kernel > 5) p->tile_kernel = 3; }
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel != 0) p->tile_kernel = 3; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;
@@ -404,4 +409,41 @@ extern "C" int tbk_decode_ffi_be(const uint8_t* raw, int B, int naxis1, int naxi
 		tbk_set_error("tbk_decode_ffi_be: bad argument"); return TBK_ERR_INVALID;
 	}
 	return tbk_launch_decode(raw, B, naxis1, naxis2, row0, col0, H, W, cube_out, (cudaStream_t)stream);
+}
+
+// Host execution of the kd-tree restatement (tbk_kdtree.cuh) for the CPU tests against scipy.spatial.cKDTree: the same
+// functions k_mesh_finalize runs on the device.  good: uint8 [ny*nx] (non-zero = good mesh).  Outputs (host pointers, any
+// may be NULL): nbr_id / nbr_d2 int32 [ny*nx][10] (-1 / -1 beyond the number of good meshes), idx_out int32 [ngood] the
+// tree's index permutation as good-point indices, nodes_out int32 [nnodes][4] = (dim, split, a, b) in creation order.
+extern "C" int tbk_debug_idw_neighbors(const uint8_t* good, int ny, int nx, int32_t* nbr_id, int32_t* nbr_d2,
+	int32_t* idx_out, int32_t* nodes_out, int32_t* nnodes_out)
+{
+	if (!good || ny <= 0 || nx <= 0 || ny * nx > 4096) { tbk_set_error("tbk_debug_idw_neighbors: bad argument"); return TBK_ERR_INVALID; }
+	const int nt = ny * nx;
+	std::vector<uint16_t> idx;
+	std::vector<int> rank_of(nt, -1);
+	for (int g = 0; g < nt; ++g) if (good[g]) { rank_of[g] = (int)idx.size(); idx.push_back((uint16_t)g); }
+	std::vector<KdtNode> nodes(2 * idx.size() + 2);
+	KdtTree t;
+	t.idx = idx.data(); t.nodes = nodes.data(); t.npts = (int)idx.size(); t.nx = nx;
+	int stack[3 * 64];
+	kdt_build(t, stack, (int)nodes.size());
+	if (t.overflow) { tbk_set_error("tbk_debug_idw_neighbors: tree overflow"); return TBK_ERR_INVALID; }
+	if (idx_out) for (int i = 0; i < t.npts; ++i) idx_out[i] = rank_of[idx[i]];
+	if (nnodes_out) *nnodes_out = t.nnodes;
+	if (nodes_out) for (int i = 0; i < t.nnodes; ++i) {
+		nodes_out[4 * i] = nodes[i].dim; nodes_out[4 * i + 1] = nodes[i].split; nodes_out[4 * i + 2] = nodes[i].a; nodes_out[4 * i + 3] = nodes[i].b;
+	}
+	if (nbr_id || nbr_d2) {
+		for (int g = 0; g < nt; ++g) {
+			int id[KDT_K], d2[KDT_K], ovf = 0;
+			const int m = kdt_query(t, g / nx, g % nx, KDT_K, id, d2, &ovf);
+			if (ovf) { tbk_set_error("tbk_debug_idw_neighbors: query queue overflow"); return TBK_ERR_INVALID; }
+			for (int j = 0; j < KDT_K; ++j) {
+				if (nbr_id) nbr_id[g * KDT_K + j] = j < m ? id[j] : -1;
+				if (nbr_d2) nbr_d2[g * KDT_K + j] = j < m ? d2[j] : -1;
+			}
+		}
+	}
+	return TBK_OK;
 }

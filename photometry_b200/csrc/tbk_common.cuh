@@ -82,7 +82,9 @@ struct Workspace {
 	double* ring_v;         // [B][nringpix] ring samples (NaN = masked)
 	float* sbmin;           // [B][ntiles][64] minimum valid pixel of every 8x8 sub-block (+inf = none)
 	float* sblow;           // [B][ntiles][64] lower bound of min(x - sq) per sub-block (zeropoint pruning)
-	int* fb_count;          // [1] meshes queued for the full-buffer statistics (TBK_TILE_KERNEL=5)
+	uint32_t* idw_bits;     // [B][1 + ceil(ntiles / 32)] valid flag + good-mesh bitmap the neighbour table was built for
+	uint16_t* idw_tab;      // [B][ntiles][10] IDW neighbours (mesh ids, 0xFFFF = none) of the excluded meshes
+	int* fb_count;          // [1] meshes queued for the full-buffer statistics
 	int* fb_list;           // [B * ntiles] queue entries b * ntiles + tile
 };
 

@@ -4,6 +4,7 @@
 #include "tbk_tile_warp.cuh"
 #include "tbk_zoom.cuh"
 #include "tbk_internal.h"
+#include "tbk_kdtree.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // K_init: per-FFI control block; manual excludes from header scalars (pixel_flags.py:34-50).
@@ -24,6 +25,7 @@ __global__ void k_init_ctl(PlanDev P, Workspace ws, const tbk_ffi_meta* __restri
 	c.kde_fallbacks = 0;
 	c.min_key = ~0ULL;
 	c.min_ub = ~0ULL;
+	ws.idw_bits[(size_t)b * ((P.ntiles + 31) / 32 + 1)] = 0u;   // no IDW neighbour table yet for this FFI
 	c.zp = 0.0; c.c_flat = 0.0; c.x0 = 0.0; c.xlast = 0.0;
 	c.mesh_min = 0.0; c.mesh_max = 0.0;
 	int mars = 0, earth = 0;
@@ -109,183 +111,10 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_base(PlanDev P, Workspace ws,
 	if (tid == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
 
-// K_tile_base_warp: same outputs as k_tile_base, one warp (= one CTA of 32 threads) per mesh, pixels in registers.
-// Lane l, load i (0..31) owns row 2i + l/16, columns 4(l%16) .. +3: every warp load covers two 256 B row segments.
-// Also records the minimum valid pixel of every 8x8 sub-block (ws.sbmin) for the pruned zeropoint pass.
-#ifndef TW_MINB
-#define TW_MINB 1
-#endif
-template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(32, TW_MINB) k_tile_base_warp(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
-{
-	__shared__ TileWarpSmem sm;
-	const int tile = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
-	const int ty = tile / P.nx, tx = tile % P.nx;
-	FfiCtl& c = ws.ctl[b];
-	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
-	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + (lane >> 4)) * P.W + gx;
-	const size_t step = (size_t)2 * P.W;
-	// manual excludes are mesh-uniform: the Mars boundary (column 1536) is a multiple of the mesh size
-	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
-	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
-
-	uint32_t v[128];
-	{
-		const float* p = cube + base;
-#pragma unroll
-		for (int i = 0; i < 32; ++i) {
-			const float4 r = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * step));
-			// x + 0.0f maps -0.0 to +0.0; non-negative finite floats then order like unsigned integers,
-			// negative / NaN / inf bit patterns all compare above the cutoff
-			v[4 * i] = __float_as_uint(r.x + 0.0f); v[4 * i + 1] = __float_as_uint(r.y + 0.0f);
-			v[4 * i + 2] = __float_as_uint(r.z + 0.0f); v[4 * i + 3] = __float_as_uint(r.w + 0.0f);
-		}
-	}
-	uint32_t nz = 0u, sb[8];
-	int nbad = 0;
-#pragma unroll
-	for (int a = 0; a < 8; ++a) sb[a] = TW_INVALID;
-#pragma unroll
-	for (int i = 0; i < 32; ++i) {
-		const size_t off = base + (size_t)i * step;
-		uint32_t ex = 0u;
-		if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
-		uint32_t m = 0u;
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const uint32_t k = v[4 * i + q];
-			nz |= k;
-			bool ok = k <= cut;
-			if (excl) ok = false;
-			if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
-			m |= ok ? 0u : (1u << (8 * q));
-			const uint32_t kv = ok ? k : TW_INVALID;
-			v[4 * i + q] = kv;
-			sb[i >> 2] = min(sb[i >> 2], kv);
-		}
-		nbad += __popc(m);
-		*reinterpret_cast<unsigned int*>(mask_out + off) = m;
-	}
-	// sub-block minima: rows 8a..8a+7 are loads 4a..4a+3; columns 8c..8c+7 are lanes {2c, 2c+1} + {0, 16}
-	uint32_t kmin = TW_INVALID;
-#pragma unroll
-	for (int a = 0; a < 8; ++a) {
-		uint32_t t = sb[a];
-		t = min(t, __shfl_xor_sync(0xffffffffu, t, 1));
-		t = min(t, __shfl_xor_sync(0xffffffffu, t, 16));
-		sb[a] = t;
-		kmin = min(kmin, t);
-	}
-	if ((lane & 17) == 0) {
-		float* dst = ws.sbmin + ((size_t)b * P.ntiles + tile) * 64 + (lane >> 1);
-#pragma unroll
-		for (int a = 0; a < 8; ++a) dst[a * 8] = __uint_as_float(sb[a]);
-	}
-	kmin = __reduce_min_sync(0xffffffffu, kmin);
-	const int n = 4096 - __reduce_add_sync(0xffffffffu, nbad);
-	nz = __reduce_or_sync(0xffffffffu, nz);
-	if (lane == 0) {
-		if (nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
-		if (n > 0) { atomicAdd(&c.n_valid, n); atomicMin(&c.min_bits, kmin); }
-	}
-	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
-	const TileStat st = tile_warp_stats(v, n, kmin, sm, lane);
-	if (lane == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
-}
-
-// K_tile_base_w2: the same work as k_tile_base_warp with two warps per mesh (64 keys per thread): half the
-// registers per thread, so twice the warps per SM to hide the latencies of the bucketing passes.
-// Thread t, load i (0..15) owns row 4i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3.
-#ifndef TW2_MINB
-#define TW2_MINB 10
-#endif
-template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(64, TW2_MINB) k_tile_base_w2(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
-{
-	__shared__ TwBlockSmem<TwF32, 2> sm;
-	__shared__ uint32_t s_sb[64];
-	__shared__ int s_nbad, s_nz;
-	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	const int ty = tile / P.nx, tx = tile % P.nx;
-	FfiCtl& c = ws.ctl[b];
-	const int gx = tx * TBK_TILE + ((lane & 15) << 2);
-	const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + 2 * w + (lane >> 4)) * P.W + gx;
-	const size_t step = (size_t)4 * P.W;
-	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
-	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
-	s_sb[tid] = TW_INVALID;
-	if (tid == 0) { s_nbad = 0; s_nz = 0; }
-
-	uint32_t v[64];
-	{
-		const float* p = cube + base;
-#pragma unroll
-		for (int i = 0; i < 16; ++i) {
-			const float4 r = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * step));
-			v[4 * i] = __float_as_uint(r.x + 0.0f); v[4 * i + 1] = __float_as_uint(r.y + 0.0f);
-			v[4 * i + 2] = __float_as_uint(r.z + 0.0f); v[4 * i + 3] = __float_as_uint(r.w + 0.0f);
-		}
-	}
-	uint32_t nz = 0u, sb[8];
-	int nbad = 0;
-#pragma unroll
-	for (int a = 0; a < 8; ++a) sb[a] = TW_INVALID;
-#pragma unroll
-	for (int i = 0; i < 16; ++i) {
-		const size_t off = base + (size_t)i * step;
-		uint32_t ex = 0u;
-		if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
-		uint32_t m = 0u;
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const uint32_t k = v[4 * i + q];
-			nz |= k;
-			bool ok = k <= cut;
-			if (excl) ok = false;
-			if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
-			m |= ok ? 0u : (1u << (8 * q));
-			const uint32_t kv = ok ? k : TW_INVALID;
-			v[4 * i + q] = kv;
-			sb[i >> 1] = min(sb[i >> 1], kv);   // rows 8a .. 8a+7 are loads 2a, 2a+1 of both warps
-		}
-		nbad += __popc(m);
-		*reinterpret_cast<unsigned int*>(mask_out + off) = m;
-	}
-	__syncthreads();
-#pragma unroll
-	for (int a = 0; a < 8; ++a) {
-		uint32_t t = sb[a];
-		t = min(t, __shfl_xor_sync(0xffffffffu, t, 1));
-		t = min(t, __shfl_xor_sync(0xffffffffu, t, 16));
-		if ((lane & 17) == 0) atomicMin(&s_sb[a * 8 + (lane >> 1)], t);
-	}
-	nbad = __reduce_add_sync(0xffffffffu, nbad);
-	nz = __reduce_or_sync(0xffffffffu, nz);
-	if (lane == 0) { atomicAdd(&s_nbad, nbad); if (nz) atomicOr(&s_nz, 1); }
-	__syncthreads();
-	const uint32_t mysb = s_sb[tid];
-	ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + tid] = __uint_as_float(mysb);
-	if (tid == 0) {
-		const int n = 4096 - s_nbad;
-		if (s_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
-		if (n > 0) atomicAdd(&c.n_valid, n);
-	}
-	if (w == 0) {
-		uint32_t kmin = min(mysb, s_sb[tid + 32]);
-		kmin = __reduce_min_sync(0xffffffffu, kmin);
-		if (lane == 0 && kmin != TW_INVALID) atomicMin(&c.min_bits, kmin);
-	}
-	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
-	TileStat st; bool writer;
-	tile_block_stats<TwF32, 2, 64>(v, sm, st, writer);
-	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
-}
-
-// K_tile_base_w3: as k_tile_base_w2, but the validated keys are staged in shared memory and the per-pixel
-// loops are rolled (small code: the unrolled register version is bound by instruction fetch).
-// Thread t, load i (0..15) owns row 4i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3.
+// K_tile_base_w3: the same outputs as k_tile_base with the bucketed algorithm of tbk_tile_warp.cuh: two warps per mesh,
+// the validated keys staged in shared memory, per-pixel loops rolled (small code: a fully unrolled register version is
+// bound by instruction fetch).  Also records the minimum valid pixel of every 8x8 sub-block (ws.sbmin) for the pruned
+// zeropoint pass.  Thread t, load i (0..15) owns row 4i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3.
 template <bool HAS_EXTRA, int NW>
 __global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
@@ -369,305 +198,6 @@ __global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Wo
 	TileStat st; bool writer;
 	tile_block_stats_staged<TwF32, NW>(sm, n, st, writer);
 	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
-}
-
-// K_tile_base_w5: the same outputs as k_tile_base_w3 with a zone-limited key buffer.  The clip iterations only ever
-// look at individual keys near the two clip bounds and near the median; every other in-window key enters through the
-// total moments alone.  So the mesh is streamed twice from global memory (the second time from L2) instead of being
-// staged: pass A builds the mask / minima and the bin counts, pass B accumulates the moments and bucket-sorts only the
-// keys of three bin ranges ("zones": below the 1.5 % quantile, mirrored above the median, and +-15 bins around the
-// median bin) into a 6 KB buffer.  10.7 KB of shared memory and no 64-key register array: more resident warps.
-// A mesh whose iterations step outside the zones (or whose zones overflow, or whose sample is degenerate) is queued
-// for k_tile_base_fb, which runs the full-buffer statistics on it.
-#define TW5_ZCAP 1536
-#ifndef TW5_MINB
-#define TW5_MINB 16
-#endif
-struct ZoneKeys {
-	const uint32_t* keys;
-	uint32_t z0e, z1s, z1e, z2s, s1, s2;
-	int* fail;
-	__device__ __forceinline__ uint32_t operator[](uint32_t p) const
-	{
-		if (p < z0e) return keys[p];
-		if (p >= z2s) return keys[p - s2];
-		if (p >= z1s && p < z1e) return keys[p - s1];
-		*fail = 1;
-		return 0u;
-	}
-};
-struct Tw5Smem {
-	uint32_t cnt[TW_CNT_WORDS];
-	uint32_t zkeys[TW5_ZCAP];
-	TwBinMap bm;
-	double pivot;
-	double red[2][2][2];
-	int ntl[2];
-	uint32_t z0e, z1s, z1e, z2s, s1, s2;
-	int BL, M0, M1, BH;
-	int fail, mode;   // mode: 0 = zoned statistics, 1 = queue for the full-buffer kernel
-};
-
-// largest bin whose start is <= P (counters hold exclusive starts right after tw_scan_counts)
-__device__ __forceinline__ int tw5_bin_of_rank(const uint32_t* cnt, uint32_t P, int lane)
-{
-	unsigned m = __ballot_sync(0xffffffffu, tw_cend(cnt, 64 * lane) <= P);
-	const int g = __popc(m) - 1;
-	m = __ballot_sync(0xffffffffu, tw_cend(cnt, 64 * g + 2 * lane) <= P);
-	const int b = 64 * g + 2 * (__popc(m) - 1);
-	return (tw_cend(cnt, b + 1) <= P) ? b + 1 : b;
-}
-
-template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(64, TW5_MINB) k_tile_base_w5(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
-{
-	__shared__ Tw5Smem sm;
-	__shared__ uint32_t s_sb[64];
-	__shared__ int s_nbad, s_nz;
-	const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	const int ty = tile / P.nx, tx = tile % P.nx;
-	FfiCtl& c = ws.ctl[b];
-	const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
-	const size_t tile0 = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE;
-	const size_t base = tile0 + (size_t)lrow0 * P.W + lcol;
-	const size_t step = (size_t)4 * P.W;
-	const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
-	const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
-	const bool do_stats = !(P.use_radial && P.tile_slot[tile] >= 0);   // those are re-evaluated every round by k_tile_round
-	s_sb[tid] = TW_INVALID;
-	for (int i = tid; i < TW_CNT_WORDS; i += 64) sm.cnt[i] = 0u;
-	if (tid == 0) { s_nbad = 0; s_nz = 0; sm.fail = 0; sm.mode = 0; }
-	// ---- robust window from 2 x 32 pixels spread over the mesh (the same positions as tile_block_stats_staged)
-	if (do_stats && w == 0) {
-		double med = 0.0, iqr = 0.0; int sets = 0;
-#pragma unroll
-		for (int t = 0; t < 2; ++t) {
-			const int idx = (lane * 131 + 17 + t * 2053) & (TBK_NPIX_TILE - 1);
-			const size_t off = tile0 + (size_t)(idx >> 6) * P.W + (idx & 63);
-			uint32_t k = __float_as_uint(__ldg(cube + off) + 0.0f);
-			bool ok = (k <= cut) && !excl;
-			if (HAS_EXTRA) ok = ok && !__ldg(extra + off);
-			k = warp_bitonic32<uint32_t>(ok ? k : TW_INVALID, lane);
-			const int m = __popc(__ballot_sync(0xffffffffu, k != TW_INVALID));
-			if (m >= 8) {
-				med += TwF32::val(__shfl_sync(0xffffffffu, k, m >> 1));
-				iqr += TwF32::val(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - TwF32::val(__shfl_sync(0xffffffffu, k, m >> 2));
-				++sets;
-			}
-		}
-		if (lane == 0) {
-			if (sets && iqr > 0.0) {
-				med /= (double)sets;
-				const double half = 10.0 * (iqr / (double)sets) / 1.349;
-				sm.bm = TwF32::make_map(med - half, med + half);
-				sm.pivot = TwF32::pivot_of(med);
-			} else sm.mode = 1;   // degenerate sample (constant or heavily tied mesh): full-buffer path
-		}
-	}
-	__syncthreads();
-	const TwBinMap bm = sm.bm;
-	const bool count = do_stats && sm.mode == 0;
-	// ---- pass A: mask, minima, bin counts
-	uint32_t nz = 0u;
-	int nbad = 0;
-	float4 nx4[2];
-	uint32_t nex[2] = {0u, 0u};
-#pragma unroll
-	for (int h = 0; h < 2; ++h) {
-		nx4[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)h * step));
-		if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(extra + base + (size_t)h * step));
-	}
-#pragma unroll 1
-	for (int a = 0; a < 8; ++a) {   // rows 8a .. 8a+7 of the mesh; the next band's loads are issued first
-		const float4 r[2] = {nx4[0], nx4[1]};
-		const uint32_t exr[2] = {nex[0], nex[1]};
-		if (a < 7) {
-#pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				nx4[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(2 * a + 2 + h) * step));
-				if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(extra + base + (size_t)(2 * a + 2 + h) * step));
-			}
-		}
-		uint32_t smin = TW_INVALID;
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			const size_t off = base + (size_t)(2 * a + h) * step;
-			const uint32_t ex = exr[h];
-			const float x4[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
-			uint32_t m = 0u;
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				const uint32_t k = __float_as_uint(x4[q] + 0.0f);   // -0.0 -> +0.0
-				nz |= k;
-				bool ok = (k <= cut) && !excl;
-				if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
-				m |= ok ? 0u : (1u << (8 * q));
-				smin = min(smin, ok ? k : TW_INVALID);
-				if (count && ok) { const int bb = TwF32::bin(bm, k); atomicAdd(&sm.cnt[TW_CIDX(bb >> 1)], 1u << ((bb & 1) << 4)); }
-			}
-			nbad += __popc(m);
-			*reinterpret_cast<unsigned int*>(mask_out + off) = m;
-		}
-		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 1));
-		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 16));
-		if ((lane & 17) == 0) atomicMin(&s_sb[a * 8 + (lane >> 1)], smin);
-	}
-	nbad = __reduce_add_sync(0xffffffffu, nbad);
-	nz = __reduce_or_sync(0xffffffffu, nz);
-	if (lane == 0) { atomicAdd(&s_nbad, nbad); if (nz) atomicOr(&s_nz, 1); }
-	__syncthreads();
-	ws.sbmin[((size_t)b * P.ntiles + tile) * 64 + tid] = __uint_as_float(s_sb[tid]);
-	const int n = 4096 - s_nbad;
-	if (tid == 0) {
-		if (s_nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
-		if (n > 0) atomicAdd(&c.n_valid, n);
-	}
-	if (w == 0) {
-		uint32_t kmin = min(s_sb[lane], s_sb[lane + 32]);
-		kmin = __reduce_min_sync(0xffffffffu, kmin);
-		if (lane == 0 && kmin != TW_INVALID) atomicMin(&c.min_bits, kmin);
-	}
-	if (!do_stats) return;
-	TileStat st;
-	st.mean = st.med = st.std = nan_d(); st.nfin = 0; st.pad = 0;
-	TileStat* dst = ws.tile_base + (size_t)b * P.ntiles + tile;
-	if (n == 0) { if (tid == 0) *dst = st; return; }
-	// ---- bin starts and the three zones (warp 0)
-	if (w == 0 && sm.mode == 0) {
-		tw_scan_counts(sm.cnt, lane);
-		__syncwarp();
-		const int mb = tw5_bin_of_rank(sm.cnt, (uint32_t)((n - 1) >> 1), lane);
-		int BL = tw5_bin_of_rank(sm.cnt, (uint32_t)((3 * n) >> 8), lane);     // ~1.2 % quantile
-		int BH = min(TW_NB - 1, mb + (mb - BL));
-		int M0 = max(mb - 15, 1), M1 = min(mb + 15, TW_NB - 2);
-		uint32_t z0e, z1s, z1e, z2s;
-		if (BL >= M0 || M1 >= BH) { z0e = z1s = z1e = z2s = (uint32_t)n; BL = TW_NB; M0 = M1 = BH = TW_NB; }   // zones touch: keep every key
-		else { z0e = tw_cend(sm.cnt, BL + 1); z1s = tw_cend(sm.cnt, M0); z1e = tw_cend(sm.cnt, M1 + 1); z2s = tw_cend(sm.cnt, BH); }
-		if (lane == 0) {
-			sm.z0e = z0e; sm.z1s = z1s; sm.z1e = z1e; sm.z2s = z2s;
-			sm.s1 = z1s - z0e; sm.s2 = (z1s - z0e) + (z2s - z1e);
-			sm.BL = BL; sm.M0 = M0; sm.M1 = M1; sm.BH = BH;
-			if (z0e + (z1e - z1s) + ((uint32_t)n - z2s) > (uint32_t)TW5_ZCAP) sm.mode = 1;
-		}
-	}
-	__syncthreads();
-	if (sm.mode != 0) {
-		if (tid == 0) ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile;
-		return;
-	}
-	// ---- pass B (L2): moments about the pivot, zone keys to their sorted-by-bin places
-	{
-		const int BL = sm.BL, M0 = sm.M0, M1 = sm.M1, BH = sm.BH;
-		const uint32_t s1 = sm.s1, s2 = sm.s2;
-		const double pivot = sm.pivot;
-		double c1 = 0.0, c2 = 0.0, q1 = 0.0, q2 = 0.0; int tn = 0;
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			nx4[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)h * step));
-			if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(extra + base + (size_t)h * step));
-		}
-#pragma unroll 1
-		for (int a = 0; a < 8; ++a) {
-			const float4 r[2] = {nx4[0], nx4[1]};
-			const uint32_t exr[2] = {nex[0], nex[1]};
-			if (a < 7) {
-#pragma unroll
-				for (int h = 0; h < 2; ++h) {
-					nx4[h] = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)(2 * a + 2 + h) * step));
-					if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(extra + base + (size_t)(2 * a + 2 + h) * step));
-				}
-			}
-#pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				const uint32_t ex = exr[h];
-				const float x4[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
-#pragma unroll
-				for (int q = 0; q < 4; ++q) {
-					const uint32_t k = __float_as_uint(x4[q] + 0.0f);
-					bool ok = (k <= cut) && !excl;
-					if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
-					if (ok) {
-						const int bb = TwF32::bin(bm, k);
-						const int sh = (bb & 1) << 4;
-						const uint32_t p = (atomicAdd(&sm.cnt[TW_CIDX(bb >> 1)], 1u << sh) >> sh) & 0xFFFFu;
-						if (bb <= BL) sm.zkeys[p] = k;
-						else if (bb >= BH) sm.zkeys[p - s2] = k;
-						else if (bb >= M0 && bb <= M1) sm.zkeys[p - s1] = k;
-						const double d = (double)__uint_as_float(k) - pivot;
-						if (bb == 0 || bb == TW_NB - 1) { ++tn; q1 += d; q2 = fma(d, d, q2); }
-						else { c1 += d; c2 = fma(d, d, c2); }
-					}
-				}
-			}
-		}
-		c1 = warp_sum_d(c1); c2 = warp_sum_d(c2);
-		tn = __reduce_add_sync(0xffffffffu, tn);
-		if (__any_sync(0xffffffffu, tn != 0)) { q1 = warp_sum_d(q1); q2 = warp_sum_d(q2); }
-		if (lane == 0) { sm.red[0][w][0] = c1; sm.red[0][w][1] = c2; sm.red[1][w][0] = q1; sm.red[1][w][1] = q2; sm.ntl[w] = tn; }
-	}
-	__syncthreads();
-	if (w != 0) return;
-	{
-		const double s1c = sm.red[0][0][0] + sm.red[0][1][0], s2c = sm.red[0][0][1] + sm.red[0][1][1];
-		const double t1 = sm.red[1][0][0] + sm.red[1][1][0], t2 = sm.red[1][0][1] + sm.red[1][1][1];
-		const int tn = sm.ntl[0] + sm.ntl[1];
-		ZoneKeys zk;
-		zk.keys = sm.zkeys; zk.z0e = sm.z0e; zk.z1s = sm.z1s; zk.z1e = sm.z1e; zk.z2s = sm.z2s; zk.s1 = sm.s1; zk.s2 = sm.s2; zk.fail = &sm.fail;
-		st = tw_iterate<TwF32, ZoneKeys>(zk, sm.cnt, bm, n, sm.pivot, s1c, s2c, tn, t1, t2, lane);
-	}
-	__syncwarp();
-	if (lane == 0) {
-		if (sm.fail) ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile;
-		else *dst = st;
-	}
-}
-
-// K_tile_base_fb: the full-buffer statistics (tile_block_stats_staged) for the meshes k_tile_base_w5 queued.
-template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(64) k_tile_base_fb(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ extra)
-{
-	__shared__ TwBlockSmem<TwF32, 2> sm;
-	__shared__ int s_n;
-	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	const int count = *ws.fb_count;
-	for (int e = blockIdx.x; e < count; e += gridDim.x) {
-		const int id = ws.fb_list[e], b = id / P.ntiles, tile = id % P.ntiles;
-		const int ty = tile / P.nx, tx = tile % P.nx;
-		const FfiCtl& c = ws.ctl[b];
-		const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
-		const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
-		const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
-		const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + lrow0) * P.W + tx * TBK_TILE + lcol;
-		if (tid == 0) s_n = 0;
-		__syncthreads();
-		int n = 0;
-		for (int i = 0; i < 16; ++i) {
-			const size_t off = base + (size_t)i * 4 * P.W;
-			const float4 r = __ldg(reinterpret_cast<const float4*>(cube + off));
-			uint32_t ex = 0u;
-			if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
-			const float x4[4] = {r.x, r.y, r.z, r.w};
-			uint32_t kk[4];
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				const uint32_t k = __float_as_uint(x4[q] + 0.0f);
-				bool ok = (k <= cut) && !excl;
-				if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
-				kk[q] = ok ? k : TW_INVALID;
-				n += ok;
-			}
-			*reinterpret_cast<uint4*>(&sm.tw.keys[(lrow0 + 4 * i) * TBK_TILE + lcol]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
-		}
-		n = __reduce_add_sync(0xffffffffu, n);
-		if (lane == 0) atomicAdd(&s_n, n);
-		__syncthreads();
-		TileStat st; bool writer;
-		tile_block_stats_staged<TwF32, 2>(sm, s_n, st, writer);
-		if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
-		__syncthreads();
-	}
 }
 
 // K_post_base: all-zero rule (pixel_flags.py:54-56), all-masked early-out (backgrounds.py:101-102),
@@ -1602,6 +1132,12 @@ __device__ __forceinline__ double median_small(double* t, int m)
 	return (m & 1) ? t[m >> 1] : 0.5 * (t[(m >> 1) - 1] + t[m >> 1]);
 }
 
+// dynamic shared memory: three double arrays + the kd-tree of the IDW fill (index permutation, nodes)
+static size_t mesh_finalize_smem(int ntiles)
+{
+	return 3 * (size_t)ntiles * sizeof(double) + sizeof(uint16_t) * (size_t)((ntiles + 3) & ~3) + sizeof(KdtNode) * (size_t)(2 * ntiles + 2);
+}
+
 __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 	tbk_ffi_status* status, int round)
 {
@@ -1646,31 +1182,66 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 		return;
 	}
 
-	// (2) IDW fill of excluded meshes: 10 nearest good meshes by (distance^2, mesh index), weights 1/d
-	for (int t = tid; t < nt_tiles; t += nt) {
-		double r = val[t];
-		if (nexcl && !(r == r)) {
-			const int iy = t / nx, ix = t % nx;
-			int bd[10]; int bi[10]; int m = 0;
-			for (int g = 0; g < nt_tiles; ++g) {
-				const double gv = val[g];
-				if (!(gv == gv)) continue;
-				const int dy = g / nx - iy, dx = g % nx - ix;
-				const int d2 = dy * dy + dx * dx;
-				if (m < 10 || d2 < bd[m - 1]) {
-					int j = (m < 10) ? m++ : 9;
-					while (j > 0 && bd[j - 1] > d2) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
-					bd[j] = d2; bi[j] = g;
-				}
-			}
-			double sw = 0.0, swv = 0.0;
-			for (int j = 0; j < m; ++j) {
-				const double wgt = 1.0 / sqrt((double)bd[j]);
-				sw += wgt; swv += wgt * val[bi[j]];
-			}
-			r = swv / sw;
+	// (2) IDW fill of excluded meshes (photutils ShepardIDWInterpolator over the 10 nearest good meshes, weights 1/d).
+	// The neighbours are the ones scipy.spatial.cKDTree(good_yx, leafsize=10).query(k=10) returns, ties included: the tree
+	// is rebuilt here exactly as scipy builds it (tbk_kdtree.cuh) -- one thread builds, every excluded mesh then searches.
+	// The neighbour table of an FFI is kept with the good-mesh bitmap it belongs to; a later round whose bitmap is the
+	// same (the usual case) reuses it.
+	if (nexcl) {
+		uint16_t* kidx = reinterpret_cast<uint16_t*>(tmp + nt_tiles);
+		KdtNode* knodes = reinterpret_cast<KdtNode*>(kidx + ((nt_tiles + 3) & ~3));
+		__shared__ KdtTree tree;
+		__shared__ int s_same, s_ovf;
+		uint32_t* bits = ws.idw_bits + (size_t)b * ((P.ntiles + 31) / 32 + 1);   // [0] = valid flag, then the bitmap
+		uint16_t* tab = ws.idw_tab + (size_t)b * P.ntiles * KDT_K;
+		const int nwords = (nt_tiles + 31) / 32;
+		if (tid == 0) { s_same = (round > 0 && bits[0] == 1u) ? 1 : 0; s_ovf = 0; }
+		__syncthreads();
+		for (int w = tid; w < nwords; w += nt) {
+			uint32_t m = 0u;
+			for (int j = 0; j < 32; ++j) { const int t = 32 * w + j; if (t < nt_tiles && val[t] == val[t]) m |= 1u << j; }
+			if (bits[1 + w] != m) { s_same = 0; bits[1 + w] = m; }
 		}
-		fil[t] = r;
+		__syncthreads();
+		const bool reuse = s_same != 0;
+		if (!reuse) {
+			if (tid == 0) {
+				int n = 0;
+				for (int t = 0; t < nt_tiles; ++t) if (val[t] == val[t]) kidx[n++] = (uint16_t)t;
+				tree.idx = kidx; tree.nodes = knodes; tree.npts = n; tree.nx = nx;
+				int stack[3 * 64];
+				kdt_build(tree, stack, 2 * nt_tiles + 2);
+				if (tree.overflow) s_ovf = 1;
+				bits[0] = 1u;
+			}
+			__syncthreads();
+		}
+		for (int t = tid; t < nt_tiles; t += nt) {
+			double r = val[t];
+			if (!(r == r)) {
+				int id[KDT_K], d2[KDT_K], m;
+				if (reuse) {
+					m = 0;
+					for (int j = 0; j < KDT_K; ++j) {
+						const int g = tab[(size_t)t * KDT_K + j];
+						if (g == 0xFFFF) break;
+						const int dy = g / nx - t / nx, dx = g % nx - t % nx;
+						id[m] = g; d2[m] = dy * dy + dx * dx; ++m;
+					}
+				} else {
+					int ovf = 0;
+					m = kdt_query(tree, t / nx, t % nx, KDT_K, id, d2, &ovf);
+					if (ovf) s_ovf = 1;
+					for (int j = 0; j < KDT_K; ++j) tab[(size_t)t * KDT_K + j] = j < m ? (uint16_t)id[j] : (uint16_t)0xFFFF;
+				}
+				r = kdt_shepard(id, d2, m, [&](int g) { return val[g]; });
+			}
+			fil[t] = r;
+		}
+		__syncthreads();
+		if (s_ovf && tid == 0 && status) status[b].n_excluded[round] = -1;   // cannot happen for <= 4096 meshes (checked by the tests)
+	} else {
+		for (int t = tid; t < nt_tiles; t += nt) fil[t] = val[t];
 	}
 	__syncthreads();
 
@@ -1891,23 +1462,11 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	const int gb = (B + 127) / 128;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
 	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 5) {
-		if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w5<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w5<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-		if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_fb<true><<<592, 64, 0, st>>>(P, ws, cube, extra)));
-		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_fb<false><<<592, 64, 0, st>>>(P, ws, cube, extra)));
-	}
-	else if (tile_kernel == 4 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 4><<<gt, 128, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 4) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 4><<<gt, 128, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 3 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 2 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<true><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (tile_kernel == 2) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w2<false><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<true><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
-	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_warp<false><<<gt, 32, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));
 	if (!launch_ok("base")) return TBK_ERR_CUDA;
-	const size_t mesh_smem = 3 * (size_t)P.ntiles * sizeof(double);
+	const size_t mesh_smem = mesh_finalize_smem(P.ntiles);
 	for (int round = 0; round < P.bkgiters; ++round) {
 		if (P.use_radial) {
 			if (round > 0) {
@@ -1950,7 +1509,7 @@ int tbk_fit_configure(void)
 {
 	cudaError_t e = cudaFuncSetAttribute(k_ring_kde, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KdeSmem));
 	if (e != cudaSuccess) { tbk_set_error("cudaFuncSetAttribute(k_ring_kde): %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
-	e = cudaFuncSetAttribute(k_mesh_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * (int)sizeof(double));
+	e = cudaFuncSetAttribute(k_mesh_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mesh_finalize_smem(4096));
 	if (e != cudaSuccess) { tbk_set_error("cudaFuncSetAttribute(k_mesh_finalize): %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
 	return TBK_OK;
 }

@@ -333,121 +333,9 @@ __device__ TileStat tw_iterate(const Keys& keys, const uint32_t* cnt, const type
 	return out;
 }
 
-// The per-warp statistics for float32 pixels.  ``v`` holds the lane's 128 pixels as float bit patterns
-// (TW_INVALID = masked), nvalid / kmin are warp-uniform.  Returns the result in every lane.
-__device__ TileStat tile_warp_stats(const uint32_t (&v)[128], int nvalid, uint32_t kmin,
-	TileWarpSmem& sm, int lane)
-{
-	TileStat out;
-	out.mean = out.med = out.std = nan_d();
-	out.nfin = 0; out.pad = 0;
-	if (nvalid == 0) return out;
-	const float vmin = __uint_as_float(kmin);
-
-	// ---- robust window from two 32-element samples spread over the mesh
-	float w0, w1, pivot_f;
-	{
-		const int sel = lane & 3;
-		const uint32_t sa = sel == 0 ? v[0] : sel == 1 ? v[37] : sel == 2 ? v[74] : v[111];
-		const uint32_t sb = sel == 0 ? v[58] : sel == 1 ? v[95] : sel == 2 ? v[4] : v[41];
-		float med = 0.f, iqr = 0.f; int sets = 0;
-#pragma unroll
-		for (int t = 0; t < 2; ++t) {
-			const uint32_t k = warp_bitonic32<uint32_t>(t ? sb : sa, lane);
-			const int m = __popc(__ballot_sync(0xffffffffu, k != TW_INVALID));
-			if (m >= 8) {
-				med += __uint_as_float(__shfl_sync(0xffffffffu, k, m >> 1));
-				iqr += __uint_as_float(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - __uint_as_float(__shfl_sync(0xffffffffu, k, m >> 2));
-				++sets;
-			}
-		}
-		if (sets && iqr > 0.f) {
-			med /= (float)sets;
-			const float half = 10.0f * (iqr / (float)sets) / 1.349f;
-			w0 = med - half; w1 = med + half;
-			pivot_f = fmaxf(med, 0.f);
-		} else {
-			// degenerate sample: use the full data range (constant meshes end here)
-			uint32_t kmax = 0u;
-#pragma unroll
-			for (int e = 0; e < 128; ++e) kmax = max(kmax, v[e] == TW_INVALID ? 0u : v[e]);
-			kmax = __reduce_max_sync(0xffffffffu, kmax);
-			if (kmax == kmin) {  // constant mesh: sigma = 0, nothing is clipped
-				out.mean = out.med = (double)vmin; out.std = 0.0; out.nfin = nvalid;
-				return out;
-			}
-			w0 = vmin; w1 = __uint_as_float(kmax); pivot_f = vmin;
-		}
-	}
-	TwBinMap bm;
-	bm.scale = (float)(TW_NB - 2) / (w1 - w0);
-	if (!(bm.scale < 1e30f)) bm.scale = 1e30f;
-	if (w0 > 0.f && w0 * bm.scale > 4194304.0f) bm.scale = 4194304.0f / w0;  // keeps off >= 2^22
-	bm.off = fmaf(-w0, bm.scale, 8388609.0f);
-	const double pivot = (double)pivot_f;
-
-	// ---- pass 1: bin counts
-	for (int i = lane; i < TW_CNT_WORDS; i += 32) sm.cnt[i] = 0u;
-	__syncwarp();
-#pragma unroll
-	for (int e = 0; e < 128; ++e) {
-		const uint32_t k = v[e];
-		const int b = TwF32::bin(bm, k);
-		if (k != TW_INVALID) atomicAdd(&sm.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4));
-	}
-	__syncwarp();
-	tw_scan_counts(sm.cnt, lane);
-	__syncwarp();
-	// ---- pass 2: scatter in groups of 8 (the counters advance from bin starts to bin ends)
-#pragma unroll
-	for (int g = 0; g < 16; ++g) {
-		uint32_t old[8]; int sh[8];
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const uint32_t k = v[8 * g + j];
-			const int b = TwF32::bin(bm, k);
-			sh[j] = (b & 1) << 4;
-			old[j] = 0u;
-			if (k != TW_INVALID) old[j] = atomicAdd(&sm.cnt[TW_CIDX(b >> 1)], 1u << sh[j]);
-		}
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const uint32_t k = v[8 * g + j];
-			if (k != TW_INVALID) sm.keys[(old[j] >> sh[j]) & 0xFFFFu] = k;
-		}
-	}
-	__syncwarp();
-
-	// ---- moments about the pivot: core bins [t0e, t1s) and the two overflow bins
-	const uint32_t t0e = tw_cend(sm.cnt, 0);
-	const uint32_t t1s = tw_cstart(sm.cnt, TW_NB - 1);
-	const uint32_t ntail = t0e + ((uint32_t)nvalid - t1s);
-	double s1c = 0.0, s2c = 0.0;
-	{
-		double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
-		uint32_t p = t0e + lane;
-		for (; p + 32 < t1s; p += 64) {
-			const double d0 = (double)__uint_as_float(sm.keys[p]) - pivot;
-			const double d1 = (double)__uint_as_float(sm.keys[p + 32]) - pivot;
-			a1 += d0; a2 = fma(d0, d0, a2); b1 += d1; b2 = fma(d1, d1, b2);
-		}
-		if (p < t1s) { const double d0 = (double)__uint_as_float(sm.keys[p]) - pivot; a1 += d0; a2 = fma(d0, d0, a2); }
-		s1c = warp_sum_d(a1 + b1); s2c = warp_sum_d(a2 + b2);
-	}
-	int tn = 0; double t1 = 0.0, t2 = 0.0;
-	for (uint32_t j = lane; j < ntail; j += 32) {
-		const uint32_t p = j < t0e ? j : t1s + (j - t0e);
-		const double d = (double)__uint_as_float(sm.keys[p]) - pivot;
-		++tn; t1 += d; t2 = fma(d, d, t2);
-	}
-	if (ntail) { tn = __reduce_add_sync(0xffffffffu, tn); t1 = warp_sum_d(t1); t2 = warp_sum_d(t2); }
-	return tw_iterate<TwF32>(sm.keys, sm.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
-}
-
 // ---------------------------------------------------------------------------------------------
-// Block version: NW warps share one mesh (VPT = 4096 / (32 NW) keys per thread in registers).  The warps
-// cooperate on the two bucketing passes and the moment sweep; warp 0 alone runs the iterations.
-// Used with NW = 4 for float64 residuals (x - radial) and NW = 2 for float32 pixels.
+// Block version: NW warps share one mesh.  The warps cooperate on the two bucketing passes and the moment sweep;
+// warp 0 alone runs the iterations.  Used with NW = 4 for float64 residuals (x - radial) and NW = 2 for float32 pixels.
 template <typename T, int NW>
 struct TwBlockSmem {
 	TwSmem<typename T::K> tw;
@@ -458,122 +346,10 @@ struct TwBlockSmem {
 	int nvalid, ntl[NW], constant;
 };
 
-template <typename T, int NW, int VPT>
-__device__ void tile_block_stats(const typename T::K (&key)[VPT], TwBlockSmem<T, NW>& sm, TileStat& out, bool& writer)
-{
-	typedef typename T::K K;
-	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	const K INV = T::invalid();
-	writer = (tid == 0);
-	out.mean = out.med = out.std = nan_d();
-	out.nfin = 0; out.pad = 0;
-	// ---- count, min, max
-	int n = 0; K kmin = T::padkey(), kmax = 0;
-#pragma unroll
-	for (int e = 0; e < VPT; ++e) {
-		const K k = key[e];
-		if (k != INV) { ++n; kmin = min(kmin, k); kmax = max(kmax, k); }
-	}
-	n = __reduce_add_sync(0xffffffffu, n);
-	for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
-	if (tid == 0) { sm.nvalid = 0; sm.kmin = T::padkey(); sm.kmax = 0; sm.constant = 0; }
-	for (int i = tid; i < TW_CNT_WORDS; i += 32 * NW) sm.tw.cnt[i] = 0u;
-	__syncthreads();
-	if (lane == 0) { atomicAdd(&sm.nvalid, n); atomicMin(&sm.kmin, kmin); atomicMax(&sm.kmax, kmax); }
-	__syncthreads();
-	const int nvalid = sm.nvalid;
-	if (nvalid == 0) return;
-	// ---- robust window from warp 0's samples (its rows are spread over the whole mesh)
-	if (w == 0) {
-		const int sel = lane & 3;
-		const K sa = sel == 0 ? key[0] : sel == 1 ? key[VPT / 4 + 1] : sel == 2 ? key[VPT / 2 + 2] : key[3 * VPT / 4 + 3];
-		const K sb = sel == 0 ? key[VPT / 2 - 2] : sel == 1 ? key[3 * VPT / 4 - 1] : sel == 2 ? key[VPT / 8] : key[VPT - 3];
-		double med = 0.0, iqr = 0.0; int sets = 0;
-#pragma unroll
-		for (int t = 0; t < 2; ++t) {
-			const K k = warp_bitonic32<K>(t ? sb : sa, lane);
-			const int m = __popc(__ballot_sync(0xffffffffu, k != INV));
-			if (m >= 8) {
-				med += T::val(__shfl_sync(0xffffffffu, k, m >> 1));
-				iqr += T::val(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - T::val(__shfl_sync(0xffffffffu, k, m >> 2));
-				++sets;
-			}
-		}
-		if (lane == 0) {
-			double w0, w1, pv;
-			const double vmin = T::val(sm.kmin), vmax = T::val(sm.kmax);
-			if (sets && iqr > 0.0) {
-				med /= (double)sets;
-				const double half = 10.0 * (iqr / (double)sets) / 1.349;
-				w0 = med - half; w1 = med + half; pv = T::pivot_of(med);
-			} else {
-				w0 = vmin; w1 = vmax; pv = vmin;
-				if (!(vmax > vmin)) sm.constant = 1;
-			}
-			sm.bm = T::make_map(w0, w1); sm.pivot = pv;
-		}
-	}
-	__syncthreads();
-	if (sm.constant) {  // all values equal: sigma = 0, nothing is clipped
-		out.mean = out.med = T::val(sm.kmin); out.std = 0.0; out.nfin = nvalid;
-		return;
-	}
-	const typename T::Map bm = sm.bm;
-	const double pivot = sm.pivot;
-	// ---- pass 1: counts
-#pragma unroll
-	for (int e = 0; e < VPT; ++e) {
-		const K k = key[e];
-		const int b = T::bin(bm, k);
-		if (k != INV) atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << ((b & 1) << 4));
-	}
-	__syncthreads();
-	if (w == 0) tw_scan_counts(sm.tw.cnt, lane);
-	__syncthreads();
-	// ---- pass 2: scatter in groups of 8
-#pragma unroll
-	for (int g = 0; g < VPT / 8; ++g) {
-		uint32_t old[8]; int sh[8];
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const K k = key[8 * g + j];
-			const int b = T::bin(bm, k);
-			sh[j] = (b & 1) << 4;
-			old[j] = 0u;
-			if (k != INV) old[j] = atomicAdd(&sm.tw.cnt[TW_CIDX(b >> 1)], 1u << sh[j]);
-		}
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const K k = key[8 * g + j];
-			if (k != INV) sm.tw.keys[(old[j] >> sh[j]) & 0xFFFFu] = k;
-		}
-	}
-	__syncthreads();
-	// ---- moments: all warps sweep the bucketed keys
-	const uint32_t t0e = tw_cend(sm.tw.cnt, 0), t1s = tw_cstart(sm.tw.cnt, TW_NB - 1);
-	double c1 = 0.0, c2 = 0.0, q1 = 0.0, q2 = 0.0; int tn = 0;
-	for (uint32_t p = tid; p < (uint32_t)nvalid; p += 32 * NW) {
-		const double d = T::val(sm.tw.keys[p]) - pivot;
-		if (p >= t0e && p < t1s) { c1 += d; c2 = fma(d, d, c2); }
-		else { ++tn; q1 += d; q2 = fma(d, d, q2); }
-	}
-	c1 = warp_sum_d(c1); c2 = warp_sum_d(c2);
-	tn = __reduce_add_sync(0xffffffffu, tn);
-	if (__any_sync(0xffffffffu, tn != 0)) { q1 = warp_sum_d(q1); q2 = warp_sum_d(q2); }
-	if (lane == 0) { sm.red[0][w][0] = c1; sm.red[0][w][1] = c2; sm.red[1][w][0] = q1; sm.red[1][w][1] = q2; sm.ntl[w] = tn; }
-	__syncthreads();
-	if (w != 0) { writer = false; return; }
-	double s1c = 0.0, s2c = 0.0, t1 = 0.0, t2 = 0.0; tn = 0;
-#pragma unroll
-	for (int q = 0; q < NW; ++q) { s1c += sm.red[0][q][0]; s2c += sm.red[0][q][1]; t1 += sm.red[1][q][0]; t2 += sm.red[1][q][1]; tn += sm.ntl[q]; }
-	out = tw_iterate<T>(sm.tw.keys, sm.tw.cnt, bm, nvalid, pivot, s1c, s2c, tn, t1, t2, lane);
-}
-
 // ---------------------------------------------------------------------------------------------
-// Staged variant: the (validated) keys of the mesh sit in sm.tw.keys in any order when this is called
-// (INVALID entries allowed), nvalid is known.  Compared with tile_block_stats the per-element passes are
-// rolled loops over shared memory -- the fully unrolled register version is ~115 KB of SASS and stalls on
-// instruction fetch -- and only the in-place scatter holds the keys in registers.
+// The (validated) keys of the mesh sit in sm.tw.keys in any order when this is called (INVALID entries allowed),
+// nvalid is known.  The per-element passes are rolled loops over shared memory (a fully unrolled register version is
+// ~115 KB of SASS and stalls on instruction fetch); only the in-place scatter holds the keys in registers.
 template <typename T, int NW>
 __device__ void tile_block_stats_staged(TwBlockSmem<T, NW>& sm, int nvalid, TileStat& out, bool& writer)
 {

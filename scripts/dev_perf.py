@@ -6,9 +6,13 @@ import photometry_b200 as pb
 from photometry_b200 import synth
 n = 512
 dev = torch.device('cuda:0')
-cube = synth.synth_stack_torch(n, 2048, 2048, dev, camera=1, ccd=2, seed=20260118)
-hdrs = [dict(CAMERA=1, CCD=2, TSTART=1400.0 + k * 0.0208, TSTOP=1400.0208 + k * 0.0208, FFIINDEX=9000 + k) for k in range(n)]
-fit = pb.BackgroundFitter((2048, 2048), True, 1, 2)
+MARS = '--mars' in sys.argv   # camera 1 / ccd 4 before cadence 4724: 8 mesh columns excluded -> IDW fill in every frame
+NOSTACK = '--no-stack' in sys.argv
+sys.argv = [a for a in sys.argv if not a.startswith('--')]
+cam, ccd, cad0 = (1, 4, 1000) if MARS else (1, 2, 9000)
+cube = synth.synth_stack_torch(n, 2048, 2048, dev, camera=cam, ccd=ccd, seed=20260118)
+hdrs = [dict(CAMERA=cam, CCD=ccd, TSTART=1400.0 + k * 0.0208, TSTOP=1400.0208 + k * 0.0208, FFIINDEX=cad0 + k) for k in range(n)]
+fit = pb.BackgroundFitter((2048, 2048), True, cam, ccd)
 meta = pb.meta_from_headers(hdrs)
 bk = torch.empty_like(cube); mk = torch.empty(cube.shape, dtype=torch.uint8, device=dev)
 for chunk in [int(a) for a in sys.argv[1:]] or [16, 64]:
@@ -24,7 +28,7 @@ for chunk in [int(a) for a in sys.argv[1:]] or [16, 64]:
 	print(f"chunk={chunk}: {n / ms * 1e3:.0f} FFIs/s ({ms / n * 1e3:.1f} us/FFI)  per-FFI us: " + ' '.join(f"{k}={v / n * 1e3:.1f}" for k, v in prof.items()), flush=True)
 
 
-for ns, chunk in ((2, 32), (2, 64), (3, 32), (4, 16), (2, 96), (2, 128), (3, 64), (4, 64)):
+for ns, chunk in (() if NOSTACK else ((2, 32), (2, 64), (3, 32), (4, 16), (3, 64), (4, 64))):
 	for rep in range(2):
 		torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True); e0.record()
 		fit.fit_stack(cube, meta, bk, mk, chunk=chunk, nstreams=ns)

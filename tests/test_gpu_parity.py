@@ -257,13 +257,15 @@ def test_full_size_properties(full_stack):
 
 
 # ---- independent implementations agree --------------------------------------------------------
+VARIANTS = ('0', '3')
+
+
 def test_kernel_variants_agree(monkeypatch):
 	"""
 	TBK_TILE_KERNEL selects independent implementations of the mesh statistics / zeropoint / ring gather
-	(0: generic CTA-per-mesh kernels with iterated histogram selection and full passes, 1: one warp per mesh,
-	2: block-cooperative bucketed kernels on registers, 3: the same with keys staged in shared memory,
-	5: zone-limited key buffer with the mesh streamed twice and a queue for the full-buffer kernel).  They must give the same statistics bit for bit in the median and
-	to rounding in mean / std, and the same backgrounds.
+	(0: generic CTA-per-mesh kernels with iterated histogram selection and full passes; 3: block-cooperative bucketed
+	kernels with the keys staged in shared memory).  They must give the same statistics bit for bit in the median and to
+	rounding in mean / std, and the same backgrounds.
 	"""
 	case = CASES['tess_small']()
 	imgs = case['images']
@@ -271,14 +273,14 @@ def test_kernel_variants_agree(monkeypatch):
 	cube = torch.from_numpy(imgs).cuda()
 	meta = pb.meta_from_headers(case['headers'])
 	res = {}
-	for variant in ('0', '1', '2', '3', '5'):
+	for variant in VARIANTS:
 		monkeypatch.setenv('TBK_TILE_KERNEL', variant)
 		fit = pb.BackgroundFitter((H, W), True, case['camera'], case['ccd'], xycen=case['xycen'], **case['fit_kwargs'])
 		bkg, mask, st = fit.fit(cube, meta)
 		ws = fit.debug_workspace()
 		res[variant] = (bkg.cpu().numpy(), mask.cpu().numpy(), ws['tile_base'].copy(), ws['tile_nf'].copy(), fit.status_to_numpy(st).copy())
 	ref = res['0']
-	for variant in ('1', '2', '3', '5'):
+	for variant in VARIANTS[1:]:
 		got = res[variant]
 		assert np.array_equal(got[1], ref[1])
 		for idx, (a, b) in enumerate(((got[2], ref[2]), (got[3], ref[3]))):

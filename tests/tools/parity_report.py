@@ -128,7 +128,7 @@ def main():
 	def log(s):
 		print(s, flush=True); lines.append(s)
 	import torch
-	log(f"Parity report, GPU path vs oracle (idw='stable'), {torch.cuda.get_device_name(0)}, seed offset {args.seed_offset}")
+	log(f"Parity report, GPU path vs oracle (idw='ckdtree': scipy.spatial.cKDTree(leafsize=10), the reference's neighbour order), {torch.cuda.get_device_name(0)}, seed offset {args.seed_offset}")
 	global BASE_SEED
 	BASE_SEED += args.seed_offset
 	with mp.get_context('spawn').Pool(args.procs) as pool:
