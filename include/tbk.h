@@ -209,7 +209,8 @@ int tbk_debug_idw_neighbors(const uint8_t* good, int ny, int nx, int32_t* nbr_id
 unsigned long long tbk_launch_count(void);
 
 /* Byte offsets of the workspace sections for a batch of B (diagnostics / tests):
- * offsets[0..7] = ctl, tile_base, tile_nf, coef, mesh_hist, s2_raw, s2_hist, ring_v;
+ * offsets[0..8] = ctl, tile_base, tile_nf, coef, mesh_hist, s2_raw, s2_hist, ring_v, fallback counters (int32 [64]: meshes
+ * the zone kernels handed to the bucketed kernels -- [0] raw-pixel statistics, [1 + round] residual statistics of a round);
  * sizes[0..2] = sizeof(FfiCtl), sizeof(TileStat), number of non-flat tiles. */
 int tbk_workspace_layout(const tbk_plan* plan, int B, size_t* offsets, size_t* sizes);
 

@@ -182,7 +182,7 @@ class BackgroundFitter:
 		"""Raw per-FFI control blocks and per-tile statistics of the most recent fit (synchronises)."""
 		ws, B = self._last
 		torch.cuda.synchronize(self.device)
-		offs = (C.c_size_t * 8)(); sizes = (C.c_size_t * 3)()
+		offs = (C.c_size_t * 9)(); sizes = (C.c_size_t * 3)()
 		check(self.lib.tbk_workspace_layout(self._plan, B, offs, sizes), 'tbk_workspace_layout')
 		raw = ws.cpu().numpy()
 		assert sizes[0] == _lib.CTL_DTYPE.itemsize and sizes[1] == _lib.TILESTAT_DTYPE.itemsize
@@ -193,7 +193,8 @@ class BackgroundFitter:
 		coef = raw[offs[3]:offs[3] + B * self.ntiles * 8].view('<f8').reshape(B, self.ntiles)
 		nr = max(self.nrings, 1)
 		s2_raw = raw[offs[5]:offs[5] + B * nr * 8].view('<f8').reshape(B, nr)[:, :self.nrings]
-		return dict(ctl=ctl, tile_base=base, tile_nf=nf, coef=coef, s2_raw=s2_raw)
+		fallbacks = raw[offs[8]:offs[8] + 64 * 4].view('<i4').copy()
+		return dict(ctl=ctl, tile_base=base, tile_nf=nf, coef=coef, s2_raw=s2_raw, fallbacks=fallbacks)
 
 	# ------------------------------------------------------------------------------------------
 	def time_smooth(self, bkg, w, halo_lo=None, halo_hi=None, out=None):

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include "tbk_common.cuh"
 #include "tbk_internal.h"
 #include "tbk_kdtree.cuh"
@@ -23,6 +25,17 @@ void tbk_set_error(const char* fmt, ...)
 extern "C" const char* tbk_last_error(void) { return g_err; }
 extern "C" int tbk_version(void) { return TBK_VERSION; }
 
+// Makes the plan's device current for the duration of an entry point and restores the caller's afterwards.
+struct DeviceGuard {
+	int prev;
+	bool switched;
+	explicit DeviceGuard(int dev) : prev(-1), switched(false)
+	{
+		if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+	}
+	~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
 	tbk_set_error("%s: %s", #x, cudaGetErrorString(e_)); return TBK_ERR_CUDA; } } while (0)
 
@@ -30,10 +43,16 @@ struct tbk_plan {
 	PlanDev dev;
 	int device;
 	std::vector<void*> allocs;
-	int* zero_flags;
-	int zero_cap;
-	int tile_kernel;   // TBK_TILE_KERNEL (development / cross-check switch): 0 = generic CTA-per-mesh kernels, 3 = bucketed kernels (default)
-	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb, off_idwbits, off_idwtab;
+	int tile_kernel;   // TBK_TILE_KERNEL (development / cross-check switch): 0 = generic CTA-per-mesh kernels, 3 = bucketed kernels, 6 = zone kernels with the bucketed ones as fallback (default)
+	std::map<cudaStream_t, TbkSide> sides;   // per caller stream (see TbkSide)
+	std::mutex mtx;
+};
+
+// Byte offsets of the workspace sections for a batch of B (a value, not plan state: a plan may serve several streams
+// and host threads with different batch sizes at once).
+struct WsLayout {
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb, off_idwbits, off_idwtab, off_rtab, off_fb2, off_zrec;
+	size_t total;
 };
 
 // photometry/backgrounds.py:121-138
@@ -76,9 +95,11 @@ static int upload(tbk_plan* p, const std::vector<T>& v, const T** out)
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void layout(tbk_plan* p, int B, size_t* total)
+static WsLayout layout(const tbk_plan* plan, int B)
 {
-	const PlanDev& P = p->dev;
+	const PlanDev& P = plan->dev;
+	WsLayout L;
+	WsLayout* p = &L;
 	size_t o = 0;
 	p->off_ctl = o;    o = align_up(o + sizeof(FfiCtl) * (size_t)B);
 	p->off_base = o;   o = align_up(o + sizeof(TileStat) * (size_t)B * P.ntiles);
@@ -93,13 +114,17 @@ static void layout(tbk_plan* p, int B, size_t* total)
 	p->off_fb = o;     o = align_up(o + 256 + sizeof(int) * (size_t)B * P.ntiles);
 	p->off_idwbits = o; o = align_up(o + sizeof(uint32_t) * (size_t)B * ((P.ntiles + 31) / 32 + 1));
 	p->off_idwtab = o; o = align_up(o + sizeof(uint16_t) * (size_t)B * P.ntiles * 10);
-	*total = o;
+	p->off_rtab = o;   o = align_up(o + sizeof(double) * 8 * (size_t)B * TBK_RSUB * std::max(P.nrings - 1, 1));
+	p->off_fb2 = o;    o = align_up(o + sizeof(int) * (size_t)B * std::max(P.n_nonflat, 1));
+	p->off_zrec = o;   o = align_up(o + ZR_REC_BYTES * (size_t)B * std::max(P.n_nonflat, 1));
+	L.total = o;
+	return L;
 }
 
-static Workspace carve(tbk_plan* p, void* base, int B)
+static Workspace carve(const tbk_plan* plan, void* base, int B)
 {
-	size_t total;
-	layout(p, B, &total);
+	const WsLayout L = layout(plan, B);
+	const WsLayout* p = &L;
 	char* b = (char*)base;
 	Workspace ws;
 	ws.ctl = (FfiCtl*)(b + p->off_ctl);
@@ -116,6 +141,9 @@ static Workspace carve(tbk_plan* p, void* base, int B)
 	ws.fb_list = (int*)(b + p->off_fb + 256);
 	ws.idw_bits = (uint32_t*)(b + p->off_idwbits);
 	ws.idw_tab = (uint16_t*)(b + p->off_idwtab);
+	ws.rtab = (double*)(b + p->off_rtab);
+	ws.fb_list2 = (int*)(b + p->off_fb2);
+	ws.zrec = (unsigned char*)(b + p->off_zrec);
 	return ws;
 }
 
@@ -139,13 +167,13 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 		else { tbk_set_error("Invalid CAMERA or CCD in header: CAMERA=%d, CCD=%d", camera, ccd); return TBK_ERR_INVALID; }
 		if (!(radial_pixel_step > 0)) { tbk_set_error("radial_pixel_step must be positive"); return TBK_ERR_INVALID; }
 	}
-	CUDA_TRY(cudaSetDevice(device));
+	{ int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { tbk_set_error("no CUDA device %d", device); return TBK_ERR_CUDA; } }
+	DeviceGuard guard(device);
 	if (tbk_fit_configure() != TBK_OK) return TBK_ERR_CUDA;
 
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
-	p->zero_flags = nullptr; p->zero_cap = 0;
-	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 3; if (p->tile_kernel != 0) p->tile_kernel = 3; }
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 6; if (p->tile_kernel != 0 && p->tile_kernel != 3) p->tile_kernel = 6; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;
@@ -158,6 +186,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	std::vector<int> ring_ptr(1, 0), ring_pix, nonflat, tile_slot(P.ntiles, -1), ringtile_id, ringtile_ptr(1, 0);
 	std::vector<unsigned> ringtile_ent;
 	std::vector<double> nonflat_r;
+	std::vector<double2> nonflat_rr;
 	if (P.use_radial) {
 		// backgrounds.py:145-154
 		std::vector<double> r((size_t)H * W);
@@ -230,10 +259,16 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 		}
 		P.n_nonflat = (int)nonflat.size();
 		nonflat_r.resize((size_t)nonflat.size() * TBK_NPIX_TILE);
+		nonflat_rr.resize(nonflat.size());
 		for (size_t k = 0; k < nonflat.size(); ++k) {
 			const int ty = nonflat[k] / P.nx, tx = nonflat[k] % P.nx;
-			for (int a = 0; a < TBK_TILE; ++a) for (int bb = 0; bb < TBK_TILE; ++bb)
-				nonflat_r[k * TBK_NPIX_TILE + a * TBK_TILE + bb] = r[(size_t)(ty * TBK_TILE + a) * W + tx * TBK_TILE + bb];
+			double lo = 1e300, hi = 0;
+			for (int a = 0; a < TBK_TILE; ++a) for (int bb = 0; bb < TBK_TILE; ++bb) {
+				const double v = r[(size_t)(ty * TBK_TILE + a) * W + tx * TBK_TILE + bb];
+				nonflat_r[k * TBK_NPIX_TILE + a * TBK_TILE + bb] = v;
+				lo = std::min(lo, v); hi = std::max(hi, v);
+			}
+			nonflat_rr[k] = make_double2(lo, hi);
 		}
 	}
 	// cubic B-spline weights per sub-tile phase (scipy ni_interpolation.c, order 3):
@@ -258,7 +293,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	if ((rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
 		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
 		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle)) ||
-		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
+		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, nonflat_rr, &P.nonflat_rr)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
 		tbk_plan_destroy(p);
 		return rc;
 	}
@@ -266,12 +301,24 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	return TBK_OK;
 }
 
+// side stream + events for the caller's stream (created on first use)
+static const TbkSide* side_for(tbk_plan* p, cudaStream_t st)
+{
+	std::lock_guard<std::mutex> lock(p->mtx);
+	auto it = p->sides.find(st);
+	if (it != p->sides.end()) return &it->second;
+	TbkSide s;
+	if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+	if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+	return &(p->sides[st] = s);
+}
+
 extern "C" int tbk_plan_destroy(tbk_plan* p)
 {
 	if (!p) return TBK_OK;
-	cudaSetDevice(p->device);
+	DeviceGuard guard(p->device);
+	for (auto& kv : p->sides) { cudaStreamDestroy(kv.second.stream); cudaEventDestroy(kv.second.fork); cudaEventDestroy(kv.second.join); }
 	for (void* d : p->allocs) cudaFree(d);
-	if (p->zero_flags) cudaFree(p->zero_flags);
 	delete p;
 	return TBK_OK;
 }
@@ -281,9 +328,7 @@ extern "C" int tbk_plan_num_rings(const tbk_plan* p) { return p ? p->dev.nrings 
 extern "C" size_t tbk_workspace_bytes(const tbk_plan* p, int B)
 {
 	if (!p || B <= 0) return 0;
-	size_t total;
-	layout(const_cast<tbk_plan*>(p), B, &total);
-	return total;
+	return layout(p, B).total;
 }
 
 extern "C" int tbk_fit_batch(tbk_plan* p, const float* cube, int B, const tbk_ffi_meta* meta,
@@ -291,13 +336,15 @@ extern "C" int tbk_fit_batch(tbk_plan* p, const float* cube, int B, const tbk_ff
 	void* workspace, void* stream)
 {
 	if (!p || !cube || !bkg_out || !mask_out || !workspace || B <= 0) { tbk_set_error("tbk_fit_batch: NULL argument or B <= 0"); return TBK_ERR_INVALID; }
+	DeviceGuard guard(p->device);
 	if (p->dev.is_tess && !meta) { tbk_set_error("tbk_fit_batch: meta is required for TESS plans"); return TBK_ERR_INVALID; }
 	if (((uintptr_t)cube | (uintptr_t)bkg_out) & 15 || ((uintptr_t)mask_out & 3) || ((uintptr_t)extra_mask & 3) || ((uintptr_t)workspace & 255)) {
 		tbk_set_error("tbk_fit_batch: misaligned pointer (cube/bkg 16 B, masks 4 B, workspace 256 B)");
 		return TBK_ERR_INVALID;
 	}
 	Workspace ws = carve(p, workspace, B);
-	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, nullptr, p->tile_kernel);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, nullptr, p->tile_kernel,
+		side_for(p, (cudaStream_t)stream));
 }
 
 extern "C" int tbk_fit_batch_profiled(tbk_plan* p, const float* cube, int B, const tbk_ffi_meta* meta,
@@ -305,8 +352,9 @@ extern "C" int tbk_fit_batch_profiled(tbk_plan* p, const float* cube, int B, con
 	void* workspace, void* stream, float* ms)
 {
 	if (!p || !cube || !bkg_out || !mask_out || !workspace || !ms || B <= 0) { tbk_set_error("tbk_fit_batch_profiled: NULL argument or B <= 0"); return TBK_ERR_INVALID; }
+	DeviceGuard guard(p->device);
 	Workspace ws = carve(p, workspace, B);
-	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, ms, p->tile_kernel);
+	return tbk_launch_fit(p->dev, ws, cube, B, meta, extra_mask, bkg_out, mask_out, status, (cudaStream_t)stream, ms, p->tile_kernel, nullptr);
 }
 
 extern "C" unsigned long long tbk_launch_count(void) { return tbk_launch_counter(); }
@@ -315,6 +363,7 @@ extern "C" int tbk_time_smooth(tbk_plan* p, const float* bkg, int n, int w,
 	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi, float* out, void* stream)
 {
 	if (!p || !bkg || !out || n <= 0 || w < 0) { tbk_set_error("tbk_time_smooth: bad argument"); return TBK_ERR_INVALID; }
+	DeviceGuard guard(p->device);
 	if ((n_lo > 0 && !halo_lo) || (n_hi > 0 && !halo_hi) || n_lo < 0 || n_hi < 0) { tbk_set_error("tbk_time_smooth: bad halo"); return TBK_ERR_INVALID; }
 	return tbk_launch_time_smooth(p->dev.H, p->dev.W, bkg, n, w, halo_lo, n_lo, halo_hi, n_hi, out, (cudaStream_t)stream);
 }
@@ -324,25 +373,27 @@ extern "C" int tbk_sum_accumulate(tbk_plan* p, const float* cube, const float* b
 	double* sum, int32_t* nimg, int32_t* used, void* stream)
 {
 	if (!p || !cube || !bkg_smooth || !flags || !meta || !sum || !nimg || !used || n <= 0) { tbk_set_error("tbk_sum_accumulate: bad argument"); return TBK_ERR_INVALID; }
-	if (n > p->zero_cap) {
-		if (p->zero_flags) CUDA_TRY(cudaFree(p->zero_flags));
-		p->zero_flags = nullptr; p->zero_cap = 0;
-		CUDA_TRY(cudaMalloc((void**)&p->zero_flags, sizeof(int) * (size_t)n));
-		p->zero_cap = n;
-	}
-	return tbk_launch_sum_accumulate(p->dev, cube, bkg_smooth, flags, meta, n, flux_out, sum, nimg, used, p->zero_flags, (cudaStream_t)stream);
+	DeviceGuard guard(p->device);
+	// per-call scratch (one flag per cadence) from the stream-ordered allocator: nothing shared between concurrent calls
+	int* zero_flags = nullptr;
+	CUDA_TRY(cudaMallocAsync((void**)&zero_flags, sizeof(int) * (size_t)n, (cudaStream_t)stream));
+	const int rc = tbk_launch_sum_accumulate(p->dev, cube, bkg_smooth, flags, meta, n, flux_out, sum, nimg, used, zero_flags, (cudaStream_t)stream);
+	cudaFreeAsync(zero_flags, (cudaStream_t)stream);
+	return rc;
 }
 
 extern "C" int tbk_sum_finalize(tbk_plan* p, const double* sum, const int32_t* nimg, const int32_t* used,
 	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, void* stream)
 {
 	if (!p || !sum || !nimg || !used || !sumimage || !pixels_used || numfiles <= 0) { tbk_set_error("tbk_sum_finalize: bad argument"); return TBK_ERR_INVALID; }
+	DeviceGuard guard(p->device);
 	return tbk_launch_sum_finalize(p->dev.H, p->dev.W, sum, nimg, used, numfiles, threshold, sumimage, pixels_used, (cudaStream_t)stream);
 }
 
 extern "C" int tbk_debug_fetch(tbk_plan* p, const void* workspace, int B, int b, int round, double* s2, double* mesh)
 {
 	if (!p || !workspace || b < 0 || b >= B || round < 0 || round >= p->dev.bkgiters) { tbk_set_error("tbk_debug_fetch: bad argument"); return TBK_ERR_INVALID; }
+	DeviceGuard guard(p->device);
 	Workspace ws = carve(p, const_cast<void*>(workspace), B);
 	const PlanDev& P = p->dev;
 	if (s2 && P.nrings > 0)
@@ -355,11 +406,10 @@ extern "C" int tbk_debug_fetch(tbk_plan* p, const void* workspace, int B, int b,
 extern "C" int tbk_workspace_layout(const tbk_plan* p, int B, size_t* offsets, size_t* sizes)
 {
 	if (!p || B <= 0 || !offsets || !sizes) { tbk_set_error("tbk_workspace_layout: bad argument"); return TBK_ERR_INVALID; }
-	size_t total;
-	tbk_plan* q = const_cast<tbk_plan*>(p);
-	layout(q, B, &total);
+	const WsLayout L = layout(p, B);
+	const WsLayout* q = &L;
 	offsets[0] = q->off_ctl; offsets[1] = q->off_base; offsets[2] = q->off_nf; offsets[3] = q->off_coef;
-	offsets[4] = q->off_mesh; offsets[5] = q->off_s2raw; offsets[6] = q->off_s2hist; offsets[7] = q->off_ringv;
+	offsets[4] = q->off_mesh; offsets[5] = q->off_s2raw; offsets[6] = q->off_s2hist; offsets[7] = q->off_ringv; offsets[8] = q->off_fb;
 	sizes[0] = sizeof(FfiCtl); sizes[1] = sizeof(TileStat); sizes[2] = (size_t)p->dev.n_nonflat;
 	return TBK_OK;
 }
@@ -420,16 +470,16 @@ extern "C" int tbk_debug_idw_neighbors(const uint8_t* good, int ny, int nx, int3
 {
 	if (!good || ny <= 0 || nx <= 0 || ny * nx > 4096) { tbk_set_error("tbk_debug_idw_neighbors: bad argument"); return TBK_ERR_INVALID; }
 	const int nt = ny * nx;
-	std::vector<uint16_t> idx;
+	std::vector<uint32_t> idx;
 	std::vector<int> rank_of(nt, -1);
-	for (int g = 0; g < nt; ++g) if (good[g]) { rank_of[g] = (int)idx.size(); idx.push_back((uint16_t)g); }
+	for (int g = 0; g < nt; ++g) if (good[g]) { rank_of[g] = (int)idx.size(); idx.push_back(kdt_pack(g, nx)); }
 	std::vector<KdtNode> nodes(2 * idx.size() + 2);
 	KdtTree t;
 	t.idx = idx.data(); t.nodes = nodes.data(); t.npts = (int)idx.size(); t.nx = nx;
 	int stack[3 * 64];
 	kdt_build(t, stack, (int)nodes.size());
 	if (t.overflow) { tbk_set_error("tbk_debug_idw_neighbors: tree overflow"); return TBK_ERR_INVALID; }
-	if (idx_out) for (int i = 0; i < t.npts; ++i) idx_out[i] = rank_of[idx[i]];
+	if (idx_out) for (int i = 0; i < t.npts; ++i) idx_out[i] = rank_of[kdt_id(idx[i])];
 	if (nnodes_out) *nnodes_out = t.nnodes;
 	if (nodes_out) for (int i = 0; i < t.nnodes; ++i) {
 		nodes_out[4 * i] = nodes[i].dim; nodes_out[4 * i + 1] = nodes[i].split; nodes_out[4 * i + 2] = nodes[i].a; nodes_out[4 * i + 3] = nodes[i].b;

@@ -30,6 +30,7 @@ struct PlanDev {
 	const int* nonflat_tiles;   // [n_nonflat] tile ids
 	const int* tile_slot;       // [ntiles] index into nonflat list or -1 (flat tile)
 	const double* nonflat_r;    // [n_nonflat][64*64] pixel radius of the non-flat meshes (static, bit-equal to pixel_radius)
+	const double2* nonflat_rr;  // [n_nonflat] (min, max) of that radius over the mesh
 	int n_ringtiles;            // meshes that contain at least one ring pixel
 	const int* ringtile_id;     // [n_ringtiles] mesh id
 	const int* ringtile_ptr;    // [n_ringtiles + 1] CSR offsets into ringtile_ent
@@ -44,6 +45,18 @@ struct TileStat {
 	int nfin;                   // pixels surviving mask + clip; nbad = 4096 - nfin
 	int pad;
 };
+
+// What k_tile_round_z leaves for k_tile_round_fin per non-flat mesh: this header, then the tails (4 quarters of ZR_TQ
+// float64) and the zone elements (4 quarters of ZR_ZQ float64).
+#define ZR_TQ 320
+#define ZR_ZQ 256
+struct ZoneRec {
+	int n, nA, nB, nZL;
+	int tq[4], zq[4];
+	int state, pad[3];          // 1 = lists complete, to be finished
+	double s1, s2, pivot, A, B, ZL, ZH, pad2;
+};
+#define ZR_REC_BYTES (sizeof(ZoneRec) + sizeof(double) * 4 * (ZR_TQ + ZR_ZQ))
 
 // Per-FFI dynamic state.
 struct FfiCtl {
@@ -82,6 +95,9 @@ struct Workspace {
 	double* ring_v;         // [B][nringpix] ring samples (NaN = masked)
 	float* sbmin;           // [B][ntiles][64] minimum valid pixel of every 8x8 sub-block (+inf = none)
 	float* sblow;           // [B][ntiles][64] lower bound of min(x - sq) per sub-block (zeropoint pruning)
+	unsigned char* zrec;    // [B][n_nonflat][ZR_REC_BYTES] lists of the residual statistics (ZoneRec + tails + zone)
+	double* rtab;           // [B][TBK_RSUB * max(nrings - 1, 1)][8] radial profile as Taylor pieces (see RadialTab)
+	int* fb_list2;          // [B * n_nonflat] queue of the residual statistics (entries b * n_nonflat + slot)
 	uint32_t* idw_bits;     // [B][1 + ceil(ntiles / 32)] valid flag + good-mesh bitmap the neighbour table was built for
 	uint16_t* idw_tab;      // [B][ntiles][10] IDW neighbours (mesh ids, 0xFFFF = none) of the excluded meshes
 	int* fb_count;          // [1] meshes queued for the full-buffer statistics
@@ -164,6 +180,80 @@ __device__ __forceinline__ void radial_stage(RadialSmem2& rs, const FfiCtl& c, c
 	}
 }
 
+// clamp without the NaN handling of fmin/fmax (v is finite)
+__device__ __forceinline__ double clamp_d(double v, double lo, double hi)
+{
+	return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// Radial profile table for the per-pixel evaluation in the residual statistics.  Every interval between two adjacent
+// ring centres is cut into TBK_RSUB pieces of width h = step / TBK_RSUB; a piece lies inside one spline piece, so
+// 10**spline(t) = exp(g(u)) with g a cubic in u = t - u0 (u0 = piece centre, |u| <= h / 2 < 1).  The row holds the Taylor
+// coefficients of exp(g) about u0 up to degree 6 (from the power-series recurrence n b_n = sum k a_k b_(n-k)), with the
+// zeropoint already subtracted from b_0, and u0:  radial(t) = b0 + u (b1 + u (b2 + ... + u b6)).  The truncated term is
+// below 1e-15 of the value for any profile the ring statistic can produce (|g'| ~ 1e-3 / px).
+#define TBK_RSUB 8
+struct RadialTab {
+	const double* rows;     // [nsub][8]: b0 - zp, b1 .. b6, u0
+	double x0, xlast, center0, inv_h;
+	int nsub, radial_ok;
+};
+__device__ __forceinline__ RadialTab radial_tab(const double* rtab_b, const FfiCtl& c, const PlanDev& P)
+{
+	RadialTab t;
+	t.rows = rtab_b; t.x0 = c.x0; t.xlast = c.xlast; t.center0 = ring_center(P, 0); t.inv_h = (double)TBK_RSUB / P.step;
+	t.nsub = TBK_RSUB * max(P.nrings - 1, 1); t.radial_ok = c.radial_ok;
+	return t;
+}
+// the same evaluation from rows [jlo, jlo + nrows) staged in shared memory (r must map into that range)
+__device__ __forceinline__ double radial_tab_eval_s(const RadialTab& t, const double* srows, int jlo, double r)
+{
+	const double tc = clamp_d(r, t.x0, t.xlast);
+	const int j = max(0, min(t.nsub - 1, (int)((tc - t.center0) * t.inv_h))) - jlo;
+	const double2* row = reinterpret_cast<const double2*>(srows + 8 * j);
+	const double2 c01 = row[0], c23 = row[1], c45 = row[2], c6u = row[3];
+	const double u = tc - c6u.y;
+	return fma(u, fma(u, fma(u, fma(u, fma(u, fma(u, c6u.x, c45.y), c45.x), c23.y), c23.x), c01.y), c01.x);
+}
+__device__ __forceinline__ double radial_tab_eval(const RadialTab& t, double r)
+{
+	const double tc = clamp_d(r, t.x0, t.xlast);
+	const int j = max(0, min(t.nsub - 1, (int)((tc - t.center0) * t.inv_h)));
+	const double2* row = reinterpret_cast<const double2*>(t.rows + 8 * (size_t)j);
+	const double2 c01 = __ldg(row), c23 = __ldg(row + 1), c45 = __ldg(row + 2), c6u = __ldg(row + 3);
+	const double u = tc - c6u.y;
+	return fma(u, fma(u, fma(u, fma(u, fma(u, fma(u, c6u.x, c45.y), c45.x), c23.y), c23.x), c01.y), c01.x);
+}
+
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) ------------------------------------
+// One thread arms the barrier with the byte count and issues the copy; the copy engine moves the bytes without any
+// register staging and flips the barrier phase when they have landed; consumers wait on the phase parity.
+__device__ __forceinline__ void tma_bar_init(unsigned long long* bar, int arrivals)
+{
+	const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(arrivals) : "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the init must be visible to the async proxy
+}
+__device__ __forceinline__ void tma_bar_expect(unsigned long long* bar, unsigned bytes)
+{
+	const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+}
+// bytes: multiple of 16; src / dst 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), a = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(d), "l"(src_gmem), "r"(bytes), "r"(a) : "memory");
+}
+__device__ __forceinline__ void tma_bar_wait(unsigned long long* bar, unsigned parity)
+{
+	const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("{\n\t.reg .pred p;\n\tTMA_WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@!p bra TMA_WAIT_%=;\n\t}" :: "r"(a), "r"(parity) : "memory");
+}
+
 #include "tbk_log10_table.cuh"
 
 // Table-driven float64 log10 for positive normal arguments (anything else takes the library path).
@@ -190,11 +280,6 @@ __device__ __forceinline__ double tbk_log10(double s, const double (*tab)[4])
 	return head + fma(r, p, fma(kd, TBK_LOG10_2_LO, tail));
 }
 
-// clamp without the NaN handling of fmin/fmax (v is finite)
-__device__ __forceinline__ double clamp_d(double v, double lo, double hi)
-{
-	return v < lo ? lo : (v > hi ? hi : v);
-}
 
 static __constant__ double c_exp_taylor[7] = {1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
 

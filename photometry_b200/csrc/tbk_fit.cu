@@ -2,6 +2,7 @@
 #include "tbk_common.cuh"
 #include "tbk_tile.cuh"
 #include "tbk_tile_warp.cuh"
+#include "tbk_tile_zone.cuh"
 #include "tbk_zoom.cuh"
 #include "tbk_internal.h"
 #include "tbk_kdtree.cuh"
@@ -11,7 +12,7 @@
 __global__ void k_init_ctl(PlanDev P, Workspace ws, const tbk_ffi_meta* __restrict__ meta, int B)
 {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b == 0) *ws.fb_count = 0;
+	if (b < 64) ws.fb_count[b] = 0;
 	if (b >= B) return;
 	FfiCtl& c = ws.ctl[b];
 	c.min_bits = 0x7f800000u;
@@ -106,7 +107,10 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_base(PlanDev P, Workspace ws,
 	}
 
 	const bool nonflat = P.use_radial && P.tile_slot[tile] >= 0;
-	if (nonflat) return;
+	if (nonflat) {   // re-evaluated every round by k_tile_round; the slot gets a defined "no statistics" entry
+		if (tid == 0) { TileStat z; z.mean = z.med = z.std = nan_d(); z.nfin = 0; z.pad = 0; ws.tile_base[(size_t)b * P.ntiles + tile] = z; }
+		return;
+	}
 	TileStat st = tile_sigma_clip<float>(v, valid, sm);
 	if (tid == 0) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
 }
@@ -194,10 +198,353 @@ __global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Wo
 		kmin = __reduce_min_sync(0xffffffffu, kmin);
 		if (lane == 0 && kmin != TW_INVALID) atomicMin(&c.min_bits, kmin);
 	}
-	if (P.use_radial && P.tile_slot[tile] >= 0) return;  // re-evaluated every round by k_tile_round
+	if (P.use_radial && P.tile_slot[tile] >= 0) {   // re-evaluated every round by k_tile_round; defined "no statistics" entry
+		if (tid == 0) { TileStat z; z.mean = z.med = z.std = nan_d(); z.nfin = 0; z.pad = 0; ws.tile_base[(size_t)b * P.ntiles + tile] = z; }
+		return;
+	}
 	TileStat st; bool writer;
 	tile_block_stats_staged<TwF32, NW>(sm, n, st, writer);
 	if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+}
+
+// K_tile_base_z: the same outputs as k_tile_base_w3 with the zone algorithm of tbk_tile_zone.cuh: one warp per mesh
+// (four meshes per CTA, no block barrier), pass 1 from HBM straight into registers, pass 2 from L2.  Lane l, load i
+// (0..31) owns row 2i + l/16, columns 4(l%16) .. +3, so every warp load covers two full 256 B row segments.
+// Meshes the lists cannot answer are queued in ws.fb_list for k_tile_base_fb.
+//
+// The per-pixel bodies are written as predicated PTX: the compiler's own if-conversion of the C++ form spends ~1.7x
+// the instructions (select-based counters, recomputed predicates, per-append address arithmetic).
+#define ZB_WARPS 4
+
+// Pass 1, one pixel.  k = float bits of x (x >= +0 when valid), ex = extra-mask byte (0 = usable).
+//   valid  = k <= cut && !ex;  kv = valid ? k : +inf key;  mask byte Q set when !valid;  smin = min(smin, kv)
+//   bulk   = kA <= kv <= kA + spanAB:  s1 += x - pivot, s2 += (x - pivot)^2  (float64; a non-bulk pixel enters as the
+//            pivot itself -- the pivot is a float32 value -- i.e. as an exact zero, which keeps the float64 adds unpredicated)
+//   tail   = valid && !bulk: appended to this lane's list (pointer tptr, stride 128 B, not stored beyond tend)
+//   nA    += kv < kA;  nM += kv < kM;  nC += kC <= kv <= kC + spanC
+template <int Q, bool HAS_EXTRA>
+__device__ __forceinline__ void zb_p1(float x, uint32_t ex, uint32_t cut, uint32_t kA, uint32_t spanAB, uint32_t kM, double pivot,
+	uint32_t& m, uint32_t& smin, int& nA, int& nM, double& s1, double& s2, uint32_t& tptr, uint32_t tend, float pivot_f,
+	uint32_t kC, uint32_t spanC, int& nC)
+{
+#define ZB_P1_HEAD \
+		".reg .pred pok, pbulk, plow, pm, pt, pst, pc;\n\t" \
+		".reg .u32 k, kv, t;\n\t" \
+		".reg .f64 d;\n\t" \
+		".reg .f32 xm;\n\t" \
+		"mov.b32 k, %9;\n\t" \
+		"setp.le.u32 pok, k, %11;\n\t"
+#define ZB_P1_TAIL \
+		"selp.u32 kv, k, 0x7f800000, pok;\n\t" \
+		"min.u32 %1, %1, kv;\n\t" \
+		"sub.u32 t, kv, %12;\n\t" \
+		"setp.le.u32 pbulk, t, %13;\n\t" \
+		"setp.lt.u32 plow, kv, %12;\n\t" \
+		"setp.lt.u32 pm, kv, %14;\n\t" \
+		"sub.u32 t, kv, %18;\n\t" \
+		"setp.le.u32 pc, t, %19;\n\t" \
+		"@plow add.s32 %2, %2, 1;\n\t" \
+		"@pm add.s32 %3, %3, 1;\n\t" \
+		"@pc add.s32 %7, %7, 1;\n\t" \
+		"selp.f32 xm, %9, %17, pbulk;\n\t" \
+		"cvt.f64.f32 d, xm;\n\t" \
+		"sub.f64 d, d, %15;\n\t" \
+		"add.f64 %4, %4, d;\n\t" \
+		"fma.rn.f64 %5, d, d, %5;\n\t" \
+		"and.pred pt, pok, !pbulk;\n\t" \
+		"setp.lt.and.u32 pst, %6, %16, pt;\n\t" \
+		"@pst st.shared.u32 [%6], kv;\n\t" \
+		"@pt add.u32 %6, %6, 128;\n\t" \
+		"@!pok or.b32 %0, %0, %8;\n\t"
+	if (HAS_EXTRA)
+		asm volatile("{\n\t" ZB_P1_HEAD "setp.eq.and.u32 pok, %10, 0, pok;\n\t" ZB_P1_TAIL "}"
+			: "+r"(m), "+r"(smin), "+r"(nA), "+r"(nM), "+d"(s1), "+d"(s2), "+r"(tptr), "+r"(nC)
+			: "n"(1u << (8 * Q)), "f"(x), "r"(ex), "r"(cut), "r"(kA), "r"(spanAB), "r"(kM), "d"(pivot), "r"(tend), "f"(pivot_f), "r"(kC), "r"(spanC) : "memory");
+	else
+		asm volatile("{\n\t" ZB_P1_HEAD ZB_P1_TAIL "}"
+			: "+r"(m), "+r"(smin), "+r"(nA), "+r"(nM), "+d"(s1), "+d"(s2), "+r"(tptr), "+r"(nC)
+			: "n"(1u << (8 * Q)), "f"(x), "r"(ex), "r"(cut), "r"(kA), "r"(spanAB), "r"(kM), "d"(pivot), "r"(tend), "f"(pivot_f), "r"(kC), "r"(spanC) : "memory");
+}
+
+// Pass 2, one pixel: zone = kZL <= kv <= kZL + zspan appended to this lane's zone list; nZL += kv < kZL.
+template <bool HAS_EXTRA>
+__device__ __forceinline__ void zb_p2(float x, uint32_t ex, uint32_t cut, uint32_t kZL, uint32_t zspan, int& nZL, uint32_t& zptr, uint32_t zend)
+{
+	if (HAS_EXTRA) {
+		asm volatile("{\n\t"
+			".reg .pred pok, pz, pl, pst;\n\t"
+			".reg .u32 k, kv, t;\n\t"
+			"mov.b32 k, %2;\n\t"
+			"setp.le.u32 pok, k, %4;\n\t"
+			"setp.eq.and.u32 pok, %3, 0, pok;\n\t"
+			"selp.u32 kv, k, 0x7f800000, pok;\n\t"
+			"sub.u32 t, kv, %5;\n\t"
+			"setp.le.u32 pz, t, %6;\n\t"
+			"setp.lt.u32 pl, kv, %5;\n\t"
+			"@pl add.s32 %0, %0, 1;\n\t"
+			"setp.lt.and.u32 pst, %1, %7, pz;\n\t"
+			"@pst st.shared.u32 [%1], kv;\n\t"
+			"@pz add.u32 %1, %1, 128;\n\t"
+			"}"
+			: "+r"(nZL), "+r"(zptr) : "f"(x), "r"(ex), "r"(cut), "r"(kZL), "r"(zspan), "r"(zend) : "memory");
+	} else {
+		// without an extra mask every key inside the zone, and every key below it, is a valid pixel (the zone lies
+		// inside [0, cutoff]; negative / NaN / inf bit patterns compare above the cutoff)
+		asm volatile("{\n\t"
+			".reg .pred pz, pl, pst;\n\t"
+			".reg .u32 k, t;\n\t"
+			"mov.b32 k, %2;\n\t"
+			"sub.u32 t, k, %3;\n\t"
+			"setp.le.u32 pz, t, %4;\n\t"
+			"setp.lt.u32 pl, k, %3;\n\t"
+			"@pl add.s32 %0, %0, 1;\n\t"
+			"setp.lt.and.u32 pst, %1, %5, pz;\n\t"
+			"@pst st.shared.u32 [%1], k;\n\t"
+			"@pz add.u32 %1, %1, 128;\n\t"
+			"}"
+			: "+r"(nZL), "+r"(zptr) : "f"(x), "r"(kZL), "r"(zspan), "r"(zend) : "memory");
+	}
+}
+
+template <bool HAS_EXTRA>
+__global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
+{
+	__shared__ ZoneSmem<Zn32> smw[ZB_WARPS];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int tile = blockIdx.x * ZB_WARPS + w, b = blockIdx.y;
+	if (tile >= P.ntiles) return;
+	ZoneSmem<Zn32>& sm = smw[w];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	FfiCtl& c = ws.ctl[b];
+	const size_t tile0 = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE;
+	const size_t base = tile0 + (size_t)(lane >> 4) * P.W + ((lane & 15) << 2);
+	const size_t step = (size_t)2 * P.W;
+	const uint32_t cut = __float_as_uint(P.flux_cutoff);
+	float* sbdst = ws.sbmin + ((size_t)b * P.ntiles + tile) * 64;
+	// manual excludes are mesh-uniform (the Mars boundary, column 1536, is a multiple of the mesh size): nothing is valid
+	if ((c.mars && tx * TBK_TILE >= 1536) || c.earth) {
+		uint32_t nz = 0u;
+		for (int i = 0; i < 32; ++i) {
+			const float4 r = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)i * step));
+			nz |= __float_as_uint(r.x + 0.0f) | __float_as_uint(r.y + 0.0f) | __float_as_uint(r.z + 0.0f) | __float_as_uint(r.w + 0.0f);
+			*reinterpret_cast<unsigned int*>(mask_out + base + (size_t)i * step) = 0x01010101u;
+		}
+		sbdst[lane] = __uint_as_float(TW_INVALID); sbdst[lane + 32] = __uint_as_float(TW_INVALID);
+		nz = __reduce_or_sync(0xffffffffu, nz);
+		if (lane == 0) {
+			if (nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+			TileStat st; st.mean = st.med = st.std = nan_d(); st.nfin = 0; st.pad = 0;
+			ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+		}
+		return;
+	}
+	const bool do_stats = !(P.use_radial && P.tile_slot[tile] >= 0);   // those are re-evaluated every round
+
+	// ---- sample: 2 x 32 pixels spread over the mesh
+	ZonePlan zp;
+	zp.ok = false; zp.mhat = 0.0; zp.shat = 1.0; zp.pivot = 0.0; zp.A = 0.0; zp.B = 0.0;
+	if (do_stats) {
+		uint32_t sk[2];
+#pragma unroll
+		for (int t = 0; t < 2; ++t) {
+			const int idx = (lane * 131 + 17 + t * 2053) & (TBK_NPIX_TILE - 1);
+			const size_t off = tile0 + (size_t)(idx >> 6) * P.W + (idx & 63);
+			const uint32_t k = __float_as_uint(__ldg(cube + off) + 0.0f);
+			bool ok = k <= cut;
+			if (HAS_EXTRA) ok = ok && !__ldg(extra + off);
+			sk[t] = ok ? k : Zn32::padkey();
+		}
+		zp = zone_plan<Zn32>(sk[0], sk[1], lane);
+	}
+	// bulk = [kA, kB] as keys; kM: keys below the sample centre.  Without a usable sample: empty bulk, every valid
+	// pixel is a "tail" (the lists overflow harmlessly and the mesh goes to the bucketed path).
+	uint32_t kA = 1u, kB = 0u, kM = 0u;
+	if (zp.ok) {
+		kA = Zn32::key_ceil(zp.A);
+		if (!Zn32::key_floor(zp.B, kB)) zp.ok = false;
+		kB = min(kB, cut);
+		kM = Zn32::key_ceil(zp.mhat);
+		if (kA > kB) zp.ok = false;
+	}
+	if (!zp.ok) { kA = 0xFFFFFFFFu; kB = 0xFFFFFFFFu; kM = 0u; }   // spanAB = 0 and kv - kA != 0 for every key: no bulk
+	const uint32_t spanAB = kB - kA;
+	// keys inside the sample centre -+ ZN_CW sigma (local density for the zone placement)
+	uint32_t kC = 0xFFFFFFFFu, kC1 = 0u;
+	if (zp.ok) { kC = Zn32::key_ceil(zp.mhat - ZN_CW * zp.shat); if (!Zn32::key_floor(zp.mhat + ZN_CW * zp.shat, kC1) || kC1 < kC) kC = 0xFFFFFFFFu; }
+	const uint32_t spanC = kC == 0xFFFFFFFFu ? 0u : kC1 - kC;
+	const double pivot = zp.pivot;
+	const float pivot_f = (float)zp.pivot;   // exact: Zn32::pivot_of returns a float32 value
+	const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(&sm.tails[lane]);
+	const uint32_t zbase = (uint32_t)__cvta_generic_to_shared(&sm.zone[lane]);
+	uint32_t tptr = tbase;
+	const uint32_t tend = do_stats ? tbase + 128u * ZN_TCAP : tbase;
+
+	// ---- pass 1: mask, flags, sub-block minima, counts, bulk moments, tails
+	uint32_t nz = 0u, kmin = TW_INVALID;
+	int nbad = 0, nA = 0, nM = 0, nC = 0;
+	double s1 = 0.0, s2 = 0.0;
+	float4 nx4[4]; uint32_t nex[4] = {0u, 0u, 0u, 0u};
+	const float* pc = cube + base;                  // this lane's pixels of the current band (bumped by 8 rows per band)
+	const uint8_t* pe = HAS_EXTRA ? extra + base : nullptr;
+	uint8_t* pm = mask_out + base;
+	const size_t band = 4 * step;
+#pragma unroll
+	for (int h = 0; h < 4; ++h) {
+		nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+		if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
+	}
+#pragma unroll 1
+	for (int a = 0; a < 8; ++a) {   // rows 8a .. 8a+7 of the mesh = loads 4a .. 4a+3; the next band's loads are issued first
+		float4 r[4]; uint32_t exr[4];
+#pragma unroll
+		for (int h = 0; h < 4; ++h) { r[h] = nx4[h]; exr[h] = nex[h]; }
+		pc += band; if (HAS_EXTRA) pe += band;
+		if (a < 7) {
+#pragma unroll
+			for (int h = 0; h < 4; ++h) {
+				nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+				if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
+			}
+		}
+		uint32_t smin = TW_INVALID;
+#pragma unroll
+		for (int h = 0; h < 4; ++h) {
+			// x + 0.0f maps -0.0 to +0.0: non-negative floats then order like unsigned integers, and negative / NaN / inf
+			// bit patterns all compare above the cutoff
+			const float x0 = r[h].x + 0.0f, x1 = r[h].y + 0.0f, x2 = r[h].z + 0.0f, x3 = r[h].w + 0.0f;
+			nz |= __float_as_uint(x0) | __float_as_uint(x1) | __float_as_uint(x2) | __float_as_uint(x3);
+			uint32_t m = 0u;
+			zb_p1<0, HAS_EXTRA>(x0, exr[h] & 0xFFu, cut, kA, spanAB, kM, pivot, m, smin, nA, nM, s1, s2, tptr, tend, pivot_f, kC, spanC, nC);
+			zb_p1<1, HAS_EXTRA>(x1, exr[h] & 0xFF00u, cut, kA, spanAB, kM, pivot, m, smin, nA, nM, s1, s2, tptr, tend, pivot_f, kC, spanC, nC);
+			zb_p1<2, HAS_EXTRA>(x2, exr[h] & 0xFF0000u, cut, kA, spanAB, kM, pivot, m, smin, nA, nM, s1, s2, tptr, tend, pivot_f, kC, spanC, nC);
+			zb_p1<3, HAS_EXTRA>(x3, exr[h] & 0xFF000000u, cut, kA, spanAB, kM, pivot, m, smin, nA, nM, s1, s2, tptr, tend, pivot_f, kC, spanC, nC);
+			nbad += __popc(m);
+			*reinterpret_cast<unsigned int*>(pm + h * step) = m;
+		}
+		pm += band;
+		// sub-block minima: columns 8c .. 8c+7 are lanes {2c, 2c+1} + {0, 16}
+		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 1));
+		smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, 16));
+		if ((lane & 17) == 0) sbdst[a * 8 + (lane >> 1)] = __uint_as_float(smin);
+		kmin = min(kmin, smin);
+	}
+	kmin = __reduce_min_sync(0xffffffffu, kmin);
+	const int n = 4096 - __reduce_add_sync(0xffffffffu, nbad);
+	nz = __reduce_or_sync(0xffffffffu, nz);
+	if (lane == 0) {
+		if (nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
+		if (n > 0) { atomicAdd(&c.n_valid, n); atomicMin(&c.min_bits, kmin); }
+	}
+	TileStat st;
+	st.mean = st.med = st.std = nan_d(); st.nfin = 0; st.pad = 0;
+	TileStat* dst = ws.tile_base + (size_t)b * P.ntiles + tile;
+	if (!do_stats || n == 0) { if (lane == 0) *dst = st; return; }
+	bool good = zp.ok && n >= ZN_MIN_N;
+	if (good) {
+		const int tcnt = (int)((tptr - tbase) >> 7);
+		const int nT = __reduce_add_sync(0xffffffffu, tcnt);
+		nA = __reduce_add_sync(0xffffffffu, nA); nM = __reduce_add_sync(0xffffffffu, nM); nC = __reduce_add_sync(0xffffffffu, nC);
+		const int nB = nT - nA;
+		s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+		double ZL, ZH;
+		zone_range(zp, n, nA, nB, nM, nC, ZL, ZH);
+		uint32_t kZL = max(Zn32::key_ceil(ZL), kA), kZH = 0u;
+		good = Zn32::key_floor(ZH, kZH);
+		kZH = min(kZH, kB);
+		good = good && kZL <= kZH;
+		if (good) {
+			// ---- pass 2 (L2): zone elements into the per-lane lists; elements below the zone are counted
+			const uint32_t zspan = kZH - kZL;
+			uint32_t zptr = zbase;
+			const uint32_t zend = zbase + 128u * ZN_ZCAP;
+			int nZL = 0;
+			pc = cube + base; if (HAS_EXTRA) pe = extra + base;
+#pragma unroll
+			for (int h = 0; h < 4; ++h) {
+				nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+				if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
+			}
+#pragma unroll 1
+			for (int a = 0; a < 8; ++a) {
+				float4 r[4]; uint32_t exr[4];
+#pragma unroll
+				for (int h = 0; h < 4; ++h) { r[h] = nx4[h]; exr[h] = nex[h]; }
+				pc += band; if (HAS_EXTRA) pe += band;
+				if (a < 7) {
+#pragma unroll
+					for (int h = 0; h < 4; ++h) {
+						nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+						if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
+					}
+				}
+#pragma unroll
+				for (int h = 0; h < 4; ++h) {
+					zb_p2<HAS_EXTRA>(r[h].x + 0.0f, exr[h] & 0xFFu, cut, kZL, zspan, nZL, zptr, zend);
+					zb_p2<HAS_EXTRA>(r[h].y + 0.0f, exr[h] & 0xFF00u, cut, kZL, zspan, nZL, zptr, zend);
+					zb_p2<HAS_EXTRA>(r[h].z + 0.0f, exr[h] & 0xFF0000u, cut, kZL, zspan, nZL, zptr, zend);
+					zb_p2<HAS_EXTRA>(r[h].w + 0.0f, exr[h] & 0xFF000000u, cut, kZL, zspan, nZL, zptr, zend);
+				}
+			}
+			nZL = __reduce_add_sync(0xffffffffu, nZL);
+			const int zcnt = (int)((zptr - zbase) >> 7);
+			const float zscale = (float)ZN_BINS / ((float)zspan + 1.0f);
+			__syncwarp();
+			good = zone_finish<Zn32>(sm, lane, n, nA, nB, nZL, tcnt, zcnt, s1, s2, pivot,
+				(double)__uint_as_float(kA), (double)__uint_as_float(kB), kZL, zscale, st);
+		}
+	}
+	if (lane == 0) {
+		if (good) *dst = st;
+		else ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile;
+	}
+}
+
+// K_tile_base_fb: bucketed statistics (tile_block_stats_staged) for the meshes k_tile_base_z queued.
+template <bool HAS_EXTRA>
+__global__ void __launch_bounds__(64) k_tile_base_fb(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra)
+{
+	__shared__ TwBlockSmem<TwF32, 2> sm;
+	__shared__ int s_n;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int count = *ws.fb_count;
+	for (int e = blockIdx.x; e < count; e += gridDim.x) {
+		const int id = ws.fb_list[e], b = id / P.ntiles, tile = id % P.ntiles;
+		const int ty = tile / P.nx, tx = tile % P.nx;
+		const FfiCtl& c = ws.ctl[b];
+		const bool excl = (c.mars && tx * TBK_TILE >= 1536) || c.earth;
+		const uint32_t cut = excl ? 0u : __float_as_uint(P.flux_cutoff);
+		const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
+		const size_t base = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + lrow0) * P.W + tx * TBK_TILE + lcol;
+		if (tid == 0) s_n = 0;
+		__syncthreads();
+		int n = 0;
+		for (int i = 0; i < 16; ++i) {
+			const size_t off = base + (size_t)i * 4 * P.W;
+			const float4 r = __ldg(reinterpret_cast<const float4*>(cube + off));
+			uint32_t ex = 0u;
+			if (HAS_EXTRA) ex = __ldg(reinterpret_cast<const unsigned int*>(extra + off));
+			const float x4[4] = {r.x, r.y, r.z, r.w};
+			uint32_t kk[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t k = __float_as_uint(x4[q] + 0.0f);
+				bool ok = k <= cut;
+				if (HAS_EXTRA) ok = ok && !((ex >> (8 * q)) & 0xFFu);
+				kk[q] = ok ? k : TW_INVALID;
+				n += ok;
+			}
+			*reinterpret_cast<uint4*>(&sm.tw.keys[(lrow0 + 4 * i) * TBK_TILE + lcol]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+		}
+		n = __reduce_add_sync(0xffffffffu, n);
+		if (lane == 0) atomicAdd(&s_n, n);
+		__syncthreads();
+		TileStat st; bool writer;
+		tile_block_stats_staged<TwF32, 2>(sm, s_n, st, writer);
+		if (writer) ws.tile_base[(size_t)b * P.ntiles + tile] = st;
+		__syncthreads();
+	}
 }
 
 // K_post_base: all-zero rule (pixel_flags.py:54-56), all-masked early-out (backgrounds.py:101-102),
@@ -607,19 +954,62 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 		const unsigned fin = __ballot_sync(0xffffffffu, d == d);
 		if (fin) { pv = __shfl_sync(0xffffffffu, d, __ffs(fin) - 1); break; }
 	}
+	// Window of the quartile histogram from a 32-element sample spread over the ring (median -+ 2.5 sample sigma: the
+	// quartiles sit at -+ 0.67 sigma).  The window only decides which bins the order statistics are looked up in -- the
+	// statistics themselves are exact -- so a poor sample costs a fallback, never accuracy.
+	const int len = hi - lo;
+	double w0 = 0.0, w1 = 0.0;
+	{
+		const int i = lo + (int)(((long long)len * (2 * (tid & 31) + 1)) >> 6);
+		const double d = len > 0 ? v[i] : nan_d();
+		const unsigned long long k = warp_bitonic32<unsigned long long>(d == d ? dkey(d) : ~0ULL, tid & 31);
+		const int m = __popc(__ballot_sync(0xffffffffu, k != ~0ULL));
+		if (m >= 16) {
+			const double med = dkey_inv(__shfl_sync(0xffffffffu, k, m >> 1));
+			const double sg = (dkey_inv(__shfl_sync(0xffffffffu, k, (3 * m) >> 2)) - dkey_inv(__shfl_sync(0xffffffffu, k, m >> 2))) / 1.349;
+			w0 = med - 2.5 * sg; w1 = med + 2.5 * sg;
+		}
+	}
+	const double hscale = (double)(TBK_NBINS - 2) / (w1 - w0);
+	const bool fast = (w1 > w0) && (hscale < 1e300);
+	const bool staged = len <= 8 * TBK_KDE_M;   // 16-bit bin per sample, overlaid on the (still unused) FFT buffer
+	uint16_t* sbin = reinterpret_cast<uint16_t*>(sm.x);
+	auto binof = [&](double d) {
+		const double t = (d - w0) * hscale;
+		return d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
+	};
+	for (int i = tid; i < TBK_NBINS; i += nt) sm.sel.hist[i] = 0u;
+	if (tid < 4) sm.qn[tid] = 0;
+	__syncthreads();
+	// ONE sweep: n, min, max, moments about the pivot, and the quartile histogram (bins kept per sample when they fit)
 	int n = 0; double mn = INFINITY, mx = -INFINITY, s1 = 0.0, ss = 0.0;
-	each([&](double d) { ++n; mn = fmin(mn, d); mx = fmax(mx, d); const double e = d - pv; s1 += e; ss = fma(e, e, ss); });
+	{
+		auto put = [&](int i, double d) {
+			int bin = 0xFFFF;
+			if (d == d) {
+				++n; mn = fmin(mn, d); mx = fmax(mx, d); const double e = d - pv; s1 += e; ss = fma(e, e, ss);
+				if (fast) { bin = binof(d); atomicAdd(&sm.sel.hist[bin], 1u); }
+			}
+			if (staged) sbin[i] = (uint16_t)bin;
+		};
+		int i = tid;
+		for (; i + 3 * nt < len; i += 4 * nt) {
+			const double d0 = v[lo + i], d1 = v[lo + i + nt], d2 = v[lo + i + 2 * nt], d3 = v[lo + i + 3 * nt];
+			put(i, d0); put(i + nt, d1); put(i + 2 * nt, d2); put(i + 3 * nt, d3);
+		}
+		for (; i < len; i += nt) put(i, v[lo + i]);
+	}
 	int nd = 0;
 	block_sum_min_max(sm.red, n, mn, mx);
 	block_sum3(sm.red, nd, s1, ss);
 	if (n <= 1) { if (tid == 0) *out = nan_d(); return; }  // reduce_mode([]) = NaN; one sample -> NaN
 	const double mean = pv + s1 / (double)n;
 	const double sd = sqrt(fmax(ss - s1 * s1 / (double)n, 0.0) / (double)(n - 1));
+	(void)mean;
 
 	// scipy.stats.scoreatpercentile(x, 25 / 75): linear interpolation at (n-1)*p.  The (up to) four order
-	// statistics are resolved together: one histogram over mean +- 1.8 std (which always brackets the
-	// quartiles), one collecting sweep; a rank whose bin is an overflow bin or too full falls back to the
-	// generic iterated selection.
+	// statistics are resolved together from the histogram of the sweep above and one collecting sweep; a rank whose
+	// bin is an overflow bin or too full falls back to the generic iterated selection.
 	double q[2];
 	{
 		int rk[4]; double fr[2];
@@ -629,39 +1019,9 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 			fr[t] = idx - (double)i0;
 			rk[2 * t] = i0; rk[2 * t + 1] = (fr[t] > 0.0) ? i0 + 1 : i0;
 		}
-		const double w0 = fmax(mean - 1.8 * sd, mn), w1 = fmin(mean + 1.8 * sd, mx);
-		const double hscale = (double)(TBK_NBINS - 2) / (w1 - w0);
-		const bool fast = (w1 > w0) && (hscale < 1e300);
 		double ord[4];
 		bool done[4] = {false, false, false, false};
-		const int len = hi - lo;
-		const bool staged = len <= 8 * TBK_KDE_M;   // 16-bit bin per sample, overlaid on the (still unused) FFT buffer
-		uint16_t* sbin = reinterpret_cast<uint16_t*>(sm.x);
 		if (fast) {
-			for (int i = tid; i < TBK_NBINS; i += nt) sm.sel.hist[i] = 0u;
-			if (tid < 4) sm.qn[tid] = 0;
-			__syncthreads();
-			auto binof = [&](double d) {
-				const double t = (d - w0) * hscale;
-				return d < w0 ? 0 : (d > w1 ? TBK_NBINS - 1 : 1 + min(TBK_NBINS - 3, (int)t));
-			};
-			if (staged) {
-				// the bin of every sample is kept (16 bit, 0xFFFF = masked) so the collecting sweep stays in shared memory
-				auto put = [&](int i, double d) {
-					int bin = 0xFFFF;
-					if (d == d) { bin = binof(d); atomicAdd(&sm.sel.hist[bin], 1u); }
-					sbin[i] = (uint16_t)bin;
-				};
-				int i = tid;
-				for (; i + 3 * nt < len; i += 4 * nt) {
-					const double d0 = v[lo + i], d1 = v[lo + i + nt], d2 = v[lo + i + 2 * nt], d3 = v[lo + i + 3 * nt];
-					put(i, d0); put(i + nt, d1); put(i + 2 * nt, d2); put(i + 3 * nt, d3);
-				}
-				for (; i < len; i += nt) put(i, v[lo + i]);
-			} else {
-				each([&](double d) { atomicAdd(&sm.sel.hist[binof(d)], 1u); });
-			}
-			__syncthreads();
 			// exclusive scan (thread t owns bins 2t, 2t+1 for 512 threads)
 			const int per = TBK_NBINS / TBK_KDE_NT;
 			unsigned loc[TBK_NBINS / TBK_KDE_NT], tsum = 0;
@@ -697,7 +1057,7 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 					if (bin == tb[0] || bin == tb[1] || bin == tb[2] || bin == tb[3]) collect(bin, v[lo + i]);
 				}
 			} else {
-				each([&](double d) { collect(binof(d), d); });
+				each([&](double d) { const int bin = binof(d); if (bin == tb[0] || bin == tb[1] || bin == tb[2] || bin == tb[3]) collect(bin, d); });
 			}
 			__syncthreads();
 			for (int r = 0; r < 4; ++r) {
@@ -745,53 +1105,103 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 	const double delta = (bb - a) / (double)(TBK_KDE_M - 1);
 	const double range = bb - a;
 
-	// linear binning (statsmodels linbin.fast_linbin): g[li] += 1 - rem, g[li+1] += rem.  Shared memory has no
-	// native 64-bit add, so each cell keeps a sample count and the sum of rem as 48-bit fixed point in three
-	// 16-bit chunks (four 32-bit atomics per sample, exact for n < 65536 and independent of the arrival
-	// order); then g[c] = count[c] - S[c] + S[c-1].  Larger rings use float64 CAS adds.
+	// linear binning (statsmodels linbin.fast_linbin): g[li] += 1 - rem, g[li+1] += rem, i.e. g[c] = count[c] - S[c] + S[c-1]
+	// with S[c] = sum of rem over the samples of cell c.  Shared memory has no native 64-bit add, so S is kept in fixed point,
+	// which also makes the result independent of the arrival order:
+	//   packed (default): two 32-bit atomics per sample -- word A = count (8 bit) | sum of the top 16 bits of rem (24 bit),
+	//     word B = sum of the next 24 bits of rem; exact to 2^-40 per sample as long as no cell holds more than 255
+	//     samples, which is verified afterwards (the count fields must add up to the number of binned samples);
+	//   fixed: four atomics per sample (count + 48-bit fraction in three 16-bit chunks), exact for n < 65536;
+	//   otherwise float64 CAS adds.
 	uint32_t* lb = reinterpret_cast<uint32_t*>(sm.x);   // [4][TBK_KDE_M] overlay on the FFT buffer
-	const bool fixed = n < 65536;
-	if (fixed) { for (int i = tid; i < 4 * TBK_KDE_M; i += nt) lb[i] = 0u; }
-	else { for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i] = make_double2(0.0, 0.0); }
-	__syncthreads();
 	// (d - a) / delta as reciprocal multiply + one fma correction (= the correctly rounded quotient); a quotient
 	// that lands within 1e-9 of an integer is recomputed with the true division so the cell index cannot differ
 	const double rdelta = 1.0 / delta;
-	each([&](double d) {
+	auto cell_of = [&](double d, int& li, double& rem) {
 		const double xa = d - a;
 		double lxi = xa * rdelta;
 		lxi = fma(fma(-lxi, delta, xa), rdelta, lxi);
-		int li = (int)lxi;
-		double rem = lxi - (double)li;
+		li = (int)lxi;
+		rem = lxi - (double)li;
 		if (rem < 1e-9 || rem > 1.0 - 1e-9) { lxi = xa / delta; li = (int)lxi; rem = lxi - (double)li; }
-		if (li > 1 && li < TBK_KDE_M - 1) {
-			if (fixed) {
-				const unsigned long long fp = (unsigned long long)(rem * 281474976710656.0);  // rem * 2^48, rem in [0, 1)
-				atomicAdd(&lb[li], 1u);
-				atomicAdd(&lb[TBK_KDE_M + li], (uint32_t)(fp & 0xFFFFu));
-				atomicAdd(&lb[2 * TBK_KDE_M + li], (uint32_t)((fp >> 16) & 0xFFFFu));
-				atomicAdd(&lb[3 * TBK_KDE_M + li], (uint32_t)(fp >> 32));
-			} else {
-				atomicAdd(&sm.x[li].x, 1.0 - rem);
-				atomicAdd(&sm.x[li + 1].x, rem);
+		return li > 1 && li < TBK_KDE_M - 1;
+	};
+	bool packed = false;
+	{
+		for (int i = tid; i < 2 * TBK_KDE_M; i += nt) lb[i] = 0u;
+		__syncthreads();
+		int nb = 0;
+		each([&](double d) {
+			int li; double rem;
+			if (cell_of(d, li, rem)) {
+				++nb;
+				const double t = rem * 65536.0;
+				const unsigned h16 = (unsigned)t;
+				const unsigned l24 = (unsigned)((t - (double)h16) * 16777216.0);
+				atomicAdd(&lb[li], (1u << 24) | h16);
+				atomicAdd(&lb[TBK_KDE_M + li], l24);
 			}
-		}
-	});
-	__syncthreads();
-	if (fixed) {
-		double g[TBK_KDE_M / TBK_KDE_NT];
-		for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) {
-			const int cidx = tid + j * nt;
-			const double S = (double)lb[TBK_KDE_M + cidx] * 3.552713678800501e-15 + (double)lb[2 * TBK_KDE_M + cidx] * 2.3283064365386963e-10
-				+ (double)lb[3 * TBK_KDE_M + cidx] * 1.52587890625e-05;
-			double Sm = 0.0;
-			if (cidx > 0) Sm = (double)lb[TBK_KDE_M + cidx - 1] * 3.552713678800501e-15 + (double)lb[2 * TBK_KDE_M + cidx - 1] * 2.3283064365386963e-10
-				+ (double)lb[3 * TBK_KDE_M + cidx - 1] * 1.52587890625e-05;
-			g[j] = ((double)lb[cidx] - S) + Sm;
-		}
+		});
 		__syncthreads();
-		for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
+		int csum = 0;
+		for (int j = tid; j < TBK_KDE_M; j += nt) csum += (int)(lb[j] >> 24);
+		double z0 = 0.0, z1 = 0.0;
+		block_sum3(sm.red, csum, z0, z1);
+		int nbt = nb;
+		block_sum3(sm.red, nbt, z0, z1);
+		packed = csum == nbt;
+		if (packed) {
+			double g[TBK_KDE_M / TBK_KDE_NT];
+			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) {
+				const int cidx = tid + j * nt;
+				const uint32_t A = lb[cidx];
+				const double S = (double)(A & 0xFFFFFFu) * 1.52587890625e-05 + (double)lb[TBK_KDE_M + cidx] * 9.094947017729282e-13;
+				double Sm = 0.0;
+				if (cidx > 0) Sm = (double)(lb[cidx - 1] & 0xFFFFFFu) * 1.52587890625e-05 + (double)lb[TBK_KDE_M + cidx - 1] * 9.094947017729282e-13;
+				g[j] = ((double)(A >> 24) - S) + Sm;
+			}
+			__syncthreads();
+			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
+			__syncthreads();
+		}
+	}
+	if (!packed) {
+		const bool fixed = n < 65536;
 		__syncthreads();
+		if (fixed) { for (int i = tid; i < 4 * TBK_KDE_M; i += nt) lb[i] = 0u; }
+		else { for (int i = tid; i < TBK_KDE_M; i += nt) sm.x[i] = make_double2(0.0, 0.0); }
+		__syncthreads();
+		each([&](double d) {
+			int li; double rem;
+			if (cell_of(d, li, rem)) {
+				if (fixed) {
+					const unsigned long long fp = (unsigned long long)(rem * 281474976710656.0);  // rem * 2^48, rem in [0, 1)
+					atomicAdd(&lb[li], 1u);
+					atomicAdd(&lb[TBK_KDE_M + li], (uint32_t)(fp & 0xFFFFu));
+					atomicAdd(&lb[2 * TBK_KDE_M + li], (uint32_t)((fp >> 16) & 0xFFFFu));
+					atomicAdd(&lb[3 * TBK_KDE_M + li], (uint32_t)(fp >> 32));
+				} else {
+					atomicAdd(&sm.x[li].x, 1.0 - rem);
+					atomicAdd(&sm.x[li + 1].x, rem);
+				}
+			}
+		});
+		__syncthreads();
+		if (fixed) {
+			double g[TBK_KDE_M / TBK_KDE_NT];
+			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) {
+				const int cidx = tid + j * nt;
+				const double S = (double)lb[TBK_KDE_M + cidx] * 3.552713678800501e-15 + (double)lb[2 * TBK_KDE_M + cidx] * 2.3283064365386963e-10
+					+ (double)lb[3 * TBK_KDE_M + cidx] * 1.52587890625e-05;
+				double Sm = 0.0;
+				if (cidx > 0) Sm = (double)lb[TBK_KDE_M + cidx - 1] * 3.552713678800501e-15 + (double)lb[2 * TBK_KDE_M + cidx - 1] * 2.3283064365386963e-10
+					+ (double)lb[3 * TBK_KDE_M + cidx - 1] * 1.52587890625e-05;
+				g[j] = ((double)lb[cidx] - S) + Sm;
+			}
+			__syncthreads();
+			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
+			__syncthreads();
+		}
 	}
 	// density = irfft(rfft(binned) * FAC): real-input transform through one 1024-point complex FFT each way
 	// (z[j] = g[2j] + i g[2j+1]).  Only the argmax is needed, so positive scale factors are dropped
@@ -1002,6 +1412,35 @@ __global__ void __launch_bounds__(32) k_radial_fit(PlanDev P, Workspace ws, tbk_
 			c.seg[i][5] = exp10(ky[sidx]);
 		}
 		if (lane == 0) { c.x0 = kx[0]; c.xlast = kx[m - 1]; c.c_flat = exp10(ky[0]) - c.zp; }
+		// Taylor pieces of 10**spline - zp for the per-pixel evaluation of the residual statistics (RadialTab)
+		{
+			const int nsub = TBK_RSUB * max(n - 1, 1);
+			const double hsub = P.step / (double)TBK_RSUB, c0 = ring_center(P, 0), zp = c.zp;
+			double* rows = ws.rtab + (size_t)b * nsub * 8;
+			for (int j = lane; j < nsub; j += 32) {
+				const double u0 = c0 + ((double)j + 0.5) * hsub;
+				const double tcl = clamp_d(u0, kx[0], kx[m - 1]);
+				int sidx = 0;
+				while (sidx + 1 < m - 1 && kx[sidx + 1] <= tcl) ++sidx;
+				const double p0 = ky[sidx], p1 = (ky[sidx + 1] - ky[sidx]) / h[sidx] - h[sidx] * (2.0 * M2[sidx] + M2[sidx + 1]) / 6.0;
+				const double p2 = 0.5 * M2[sidx], p3 = (M2[sidx + 1] - M2[sidx]) / (6.0 * h[sidx]);
+				const double s0 = tcl - kx[sidx];
+				const double LN10 = 2.302585092994045684;
+				const double yv = p0 + s0 * (p1 + s0 * (p2 + s0 * p3));
+				const double a1 = LN10 * (p1 + s0 * (2.0 * p2 + 3.0 * s0 * p3)), a2 = LN10 * (p2 + 3.0 * s0 * p3), a3 = LN10 * p3;
+				double bb[7];
+				bb[0] = exp10(yv);
+				for (int q = 1; q <= 6; ++q) {
+					double acc = a1 * bb[q - 1];
+					if (q >= 2) acc += 2.0 * a2 * bb[q - 2];
+					if (q >= 3) acc += 3.0 * a3 * bb[q - 3];
+					bb[q] = acc / (double)q;
+				}
+				rows[8 * j] = bb[0] - zp;
+				for (int q = 1; q <= 6; ++q) rows[8 * j + q] = bb[q];
+				rows[8 * j + 7] = tcl;
+			}
+		}
 		ok = 1;
 	}
 	// m == 3: FITPACK raises "m must be > k" (caught, backgrounds.py:192-194); m < 3: not enough points.
@@ -1063,14 +1502,20 @@ __global__ void __launch_bounds__(TBK_NT) k_tile_round(PlanDev P, Workspace ws,
 #ifndef TWR_MINB
 #define TWR_MINB 5
 #endif
+template <bool QUEUE>
 __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ mask)
+	const float* __restrict__ cube, const uint8_t* __restrict__ mask, int round)
 {
 	__shared__ TwBlockSmem<TwF64, 4> sm;
 	__shared__ RadialSmem2 rs;
-	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const int tid = threadIdx.x;
+	// QUEUE: work off the meshes k_tile_round_z queued (grid-stride over ws.fb_list2); otherwise one CTA per (mesh, FFI)
+	const int count = QUEUE ? ws.fb_count[1 + round] : 1;
+	for (int e = QUEUE ? blockIdx.x : 0; e < count; e += QUEUE ? gridDim.x : 1) {
+	const int slot = QUEUE ? ws.fb_list2[e] % P.n_nonflat : blockIdx.x, b = QUEUE ? ws.fb_list2[e] / P.n_nonflat : blockIdx.y;
 	const FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
+	__syncthreads();
 	radial_stage(rs, c, P);
 	__syncthreads();
 	const int tile = P.nonflat_tiles[slot];
@@ -1116,6 +1561,247 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 	TileStat st; bool writer;
 	tile_block_stats_staged<TwF64, 4>(sm, s_n, st, writer);
 	if (writer) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
+	}
+}
+
+// K_tile_round_z / K_tile_round_fin: the residual statistics (x - radial(r), float64) of the non-flat meshes with the zone
+// algorithm of tbk_tile_zone.cuh, in two kernels.
+//   k_tile_round_z   one CTA of 128 threads per mesh: the residuals are evaluated once (Taylor-piece table of the round,
+//                    RadialTab) and staged in shared memory; the two classification passes of the four warps run over the
+//                    staged values; every warp appends its tails / zone elements to its own quarter of the mesh's lists
+//                    in global memory by ballot prefix (no atomics: the lists do not depend on timing).
+//   k_tile_round_fin one warp per mesh finishes from those lists (clip iterations on the tails, medians from the zone).
+// The finish phase is serial work of one warp (a few thousand dependent instructions); as a kernel of its own it runs at
+// ~24 warps per SM instead of idling three of four warps of the producer CTA.
+// Meshes the lists cannot answer are queued in ws.fb_list2 for k_tile_round_w<true>.
+#define ZR_ROWS 56
+struct ZoneRoundSmem {
+	double d[TBK_NPIX_TILE];          // staged residuals, NaN = masked
+	double rows[ZR_ROWS][8];          // the Taylor pieces this mesh can see (RadialTab rows jlo .. jlo + ZR_ROWS - 1)
+	unsigned long long bar;           // mbarrier of the TMA copy of the mesh's radius tile
+	double red[4][2];
+	int redi[4][4];
+	double A, B, M, pivot, shat, mhat;
+	int ok, n;
+};
+
+__global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws,
+	const float* __restrict__ cube, const uint8_t* __restrict__ mask, int round)
+{
+	__shared__ __align__(16) ZoneRoundSmem sm;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int slot = blockIdx.x, b = blockIdx.y;
+	const FfiCtl& c = ws.ctl[b];
+	ZoneRec& rec = *reinterpret_cast<ZoneRec*>(ws.zrec + ((size_t)b * P.n_nonflat + slot) * ZR_REC_BYTES);
+	if (c.all_masked || c.no_good_mesh) { if (tid == 0) rec.state = 0; return; }
+	const RadialTab rt = radial_tab(ws.rtab + (size_t)b * TBK_RSUB * max(P.nrings - 1, 1) * 8, c, P);
+	const int tile = P.nonflat_tiles[slot];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	// The static radius tile of the mesh (32 KB, contiguous) comes in through the TMA engine (one cp.async.bulk into sm.d,
+	// the residuals later overwrite it in place); meanwhile every thread has all of its pixel / mask loads in flight at once
+	// and the Taylor pieces between the smallest and largest radius of the mesh are staged (a mesh spans < 91 px).
+	if (tid == 0) {
+		tma_bar_init(&sm.bar, 1);
+		tma_bar_expect(&sm.bar, (unsigned)(TBK_NPIX_TILE * sizeof(double)));
+		tma_load_1d(sm.d, P.nonflat_r + (size_t)slot * TBK_NPIX_TILE, (unsigned)(TBK_NPIX_TILE * sizeof(double)), &sm.bar);
+	}
+	// thread t, step i (0..7) owns row 8i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3
+	const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
+	float4 xs[8]; unsigned int mks[8];
+	{
+		const size_t off0 = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE + lrow0) * P.W + tx * TBK_TILE + lcol;
+		const size_t step = (size_t)8 * P.W;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			xs[i] = __ldg(reinterpret_cast<const float4*>(cube + off0 + i * step));
+			mks[i] = __ldg(reinterpret_cast<const unsigned int*>(mask + off0 + i * step));
+		}
+	}
+	int jlo = 0;
+	if (rt.radial_ok) {
+		const double2 rr = __ldg(P.nonflat_rr + slot);
+		jlo = max(0, min(rt.nsub - 1, (int)((clamp_d(rr.x, rt.x0, rt.xlast) - rt.center0) * rt.inv_h)) - 1);
+		const int jhi = min(rt.nsub - 1, max(0, min(rt.nsub - 1, (int)((clamp_d(rr.y, rt.x0, rt.xlast) - rt.center0) * rt.inv_h))) + 1);
+		if (jhi - jlo + 1 > ZR_ROWS) {   // cannot happen for meshes of 64 px and step / 8 >= 1.75 px; other parameters: bucketed path
+			__syncthreads();
+			if (tid == 0) { tma_bar_wait(&sm.bar, 0u); rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
+			return;
+		}
+		for (int e = tid; e < (jhi - jlo + 1) * 4; e += 128)
+			reinterpret_cast<double2*>(&sm.rows[0][0])[e] = __ldg(reinterpret_cast<const double2*>(rt.rows + 8 * (size_t)jlo) + e);
+	}
+	__syncthreads();                 // rows staged, barrier initialised
+	tma_bar_wait(&sm.bar, 0u);       // radius tile landed
+	{
+		const double cflat = rt.radial_ok ? radial_tab_eval_s(rt, &sm.rows[0][0], jlo, rt.x0) : 0.0;   // radial(r) for r <= x0 (ext=3 clamp)
+		int n = 0;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			double2* cell = reinterpret_cast<double2*>(&sm.d[(lrow0 + 8 * i) * TBK_TILE + lcol]);
+			const double2 r01 = cell[0], r23 = cell[1];
+			const float x4[4] = {xs[i].x, xs[i].y, xs[i].z, xs[i].w};
+			const double rr[4] = {r01.x, r01.y, r23.x, r23.y};
+			double dd[4];
+			// inside r <= x0 the profile is the constant cflat: the whole warp skips the evaluation there
+			const bool beyond = rt.radial_ok && __any_sync(0xffffffffu, rr[3] > rt.x0 || rr[0] > rt.x0);
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const bool ok = !((mks[i] >> (8 * q)) & 0xFFu);
+				const double rad = beyond ? radial_tab_eval_s(rt, &sm.rows[0][0], jlo, rr[q]) : cflat;
+				dd[q] = ok ? (double)x4[q] - rad : nan_d();
+				n += ok;
+			}
+			cell[0] = make_double2(dd[0], dd[1]); cell[1] = make_double2(dd[2], dd[3]);
+		}
+		n = __reduce_add_sync(0xffffffffu, n);
+		if (lane == 0) sm.redi[w][0] = n;
+	}
+	__syncthreads();
+	// ---- sample (warp 0): 2 x 32 staged residuals spread over the mesh
+	if (w == 0) {
+		unsigned long long sk[2];
+#pragma unroll
+		for (int t = 0; t < 2; ++t) {
+			const double v = sm.d[(lane * 131 + 17 + t * 2053) & (TBK_NPIX_TILE - 1)];
+			sk[t] = (v == v) ? dkey(v) : Zn64::padkey();
+		}
+		const ZonePlan zp = zone_plan<Zn64>(sk[0], sk[1], lane);
+		if (lane == 0) {
+			sm.ok = zp.ok; sm.A = zp.A; sm.B = zp.B; sm.M = zp.mhat; sm.mhat = zp.mhat; sm.shat = zp.shat; sm.pivot = zp.pivot;
+			sm.n = sm.redi[0][0] + sm.redi[1][0] + sm.redi[2][0] + sm.redi[3][0];
+		}
+	}
+	__syncthreads();
+	const int n = sm.n;
+	if (n == 0) {
+		if (tid == 0) {
+			TileStat st; st.mean = st.med = st.std = nan_d(); st.nfin = 0; st.pad = 0;
+			ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
+			rec.state = 0;
+		}
+		return;
+	}
+	if (!sm.ok || n < ZN_MIN_N) {
+		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
+		return;
+	}
+	const double A = sm.A, Bv = sm.B, M = sm.M, pivot = sm.pivot;
+	const unsigned lt = (1u << lane) - 1u;
+	double* gt = reinterpret_cast<double*>(reinterpret_cast<char*>(&rec) + sizeof(ZoneRec));
+	double* gz = gt + 4 * ZR_TQ;
+	// ---- pass 1 over the staged values (element j * 128 + t): counts, bulk moments, tails in (j, lane) order
+	{
+		int nA = 0, nM = 0, nC = 0, tpos = 0;
+		double s1 = 0.0, s2 = 0.0;
+		double* gtw = gt + w * ZR_TQ;
+		const double C0 = M - ZN_CW * sm.shat, C1 = M + ZN_CW * sm.shat;
+#pragma unroll 4
+		for (int j = 0; j < TBK_NPIX_TILE / 128; ++j) {
+			const double d = sm.d[j * 128 + tid];
+			const bool bulk = d >= A && d <= Bv;       // false for NaN
+			const bool isT = d == d && !bulk;
+			nA += (d < A); nM += (d < M); nC += (d >= C0 && d <= C1);
+			const double e = (bulk ? d : pivot) - pivot;
+			s1 += e; s2 = fma(e, e, s2);
+			const unsigned mT = __ballot_sync(0xffffffffu, isT);
+			const int pos = tpos + __popc(mT & lt);
+			if (isT && pos < ZR_TQ) gtw[pos] = d;
+			tpos += __popc(mT);
+		}
+		nA = __reduce_add_sync(0xffffffffu, nA); nM = __reduce_add_sync(0xffffffffu, nM); nC = __reduce_add_sync(0xffffffffu, nC);
+		s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+		if (lane == 0) { sm.redi[w][0] = nC; sm.redi[w][1] = nA; sm.redi[w][2] = nM; sm.redi[w][3] = tpos; sm.red[w][0] = s1; sm.red[w][1] = s2; }
+	}
+	__syncthreads();
+	const int nC = sm.redi[0][0] + sm.redi[1][0] + sm.redi[2][0] + sm.redi[3][0];
+	const int nA = sm.redi[0][1] + sm.redi[1][1] + sm.redi[2][1] + sm.redi[3][1];
+	const int nM = sm.redi[0][2] + sm.redi[1][2] + sm.redi[2][2] + sm.redi[3][2];
+	const int tq[4] = {sm.redi[0][3], sm.redi[1][3], sm.redi[2][3], sm.redi[3][3]};
+	const int nB = tq[0] + tq[1] + tq[2] + tq[3] - nA;
+	const double s1 = (sm.red[0][0] + sm.red[1][0]) + (sm.red[2][0] + sm.red[3][0]);
+	const double s2 = (sm.red[0][1] + sm.red[1][1]) + (sm.red[2][1] + sm.red[3][1]);
+	ZonePlan zp;
+	zp.ok = true; zp.mhat = sm.mhat; zp.shat = sm.shat; zp.pivot = pivot; zp.A = A; zp.B = Bv;
+	double ZL, ZH;
+	zone_range(zp, n, nA, nB, nM, nC, ZL, ZH);
+	const bool tail_ovf = tq[0] > ZR_TQ || tq[1] > ZR_TQ || tq[2] > ZR_TQ || tq[3] > ZR_TQ;
+	if (!(ZL < ZH) || tail_ovf || n - nA - nB <= 0) {
+		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
+		return;
+	}
+	__syncthreads();   // redi is reused below
+	// ---- pass 2: zone elements into the warp's quarter of the zone list; elements below the zone are counted
+	{
+		int nZL = 0, zpos = 0;
+		double* gzw = gz + w * ZR_ZQ;
+#pragma unroll 4
+		for (int j = 0; j < TBK_NPIX_TILE / 128; ++j) {
+			const double d = sm.d[j * 128 + tid];
+			nZL += (d < ZL);
+			const bool isZ = d >= ZL && d <= ZH;
+			const unsigned mZ = __ballot_sync(0xffffffffu, isZ);
+			const int pos = zpos + __popc(mZ & lt);
+			if (isZ && pos < ZR_ZQ) gzw[pos] = d;
+			zpos += __popc(mZ);
+		}
+		nZL = __reduce_add_sync(0xffffffffu, nZL);
+		if (lane == 0) { sm.redi[w][0] = nZL; sm.redi[w][1] = zpos; }
+	}
+	__syncthreads();
+	if (tid != 0) return;
+	const int zq[4] = {sm.redi[0][1], sm.redi[1][1], sm.redi[2][1], sm.redi[3][1]};
+	if (zq[0] > ZR_ZQ || zq[1] > ZR_ZQ || zq[2] > ZR_ZQ || zq[3] > ZR_ZQ || zq[0] + zq[1] + zq[2] + zq[3] == 0) {
+		rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot;
+		return;
+	}
+	rec.n = n; rec.nA = nA; rec.nB = nB; rec.nZL = sm.redi[0][0] + sm.redi[1][0] + sm.redi[2][0] + sm.redi[3][0];
+	for (int q = 0; q < 4; ++q) { rec.tq[q] = tq[q]; rec.zq[q] = zq[q]; }
+	rec.s1 = s1; rec.s2 = s2; rec.pivot = pivot; rec.A = A; rec.B = Bv; rec.ZL = ZL; rec.ZH = ZH;
+	rec.state = 1;
+}
+
+#define ZF_WARPS 4
+#define ZF_TCAP 768
+#define ZF_ZCAP 512
+struct ZoneFinSmem {
+	double tails[ZF_TCAP];
+	unsigned long long zone[ZF_ZCAP];
+	uint32_t cnt[ZN_BINS];
+};
+__global__ void __launch_bounds__(32 * ZF_WARPS, 5) k_tile_round_fin(PlanDev P, Workspace ws, int round)
+{
+	__shared__ ZoneFinSmem smw[ZF_WARPS];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int slot = blockIdx.x * ZF_WARPS + w, b = blockIdx.y;
+	if (slot >= P.n_nonflat) return;
+	const ZoneRec& rec = *reinterpret_cast<const ZoneRec*>(ws.zrec + ((size_t)b * P.n_nonflat + slot) * ZR_REC_BYTES);
+	if (rec.state != 1) return;
+	ZoneFinSmem& sm = smw[w];
+	const double* gt = reinterpret_cast<const double*>(reinterpret_cast<const char*>(&rec) + sizeof(ZoneRec));
+	const double* gz = gt + 4 * ZR_TQ;
+	const int tq[4] = {rec.tq[0], rec.tq[1], rec.tq[2], rec.tq[3]}, zq[4] = {rec.zq[0], rec.zq[1], rec.zq[2], rec.zq[3]};
+	const int nT = tq[0] + tq[1] + tq[2] + tq[3], nZ = zq[0] + zq[1] + zq[2] + zq[3];
+	const double ZL = rec.ZL, ZH = rec.ZH;
+	const float zscale = (float)ZN_BINS / (float)(ZH - ZL) * 0.99999f;
+	TileStat st;
+	bool good = nT <= ZF_TCAP && nZ <= ZF_ZCAP;
+	if (good) {
+		// tails: the four quarters -> one dense list in shared memory (they are swept once per clip iteration)
+		int dstT = 0;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			for (int i = lane; i < tq[q]; i += 32) sm.tails[dstT + i] = gt[q * ZR_TQ + i];
+			dstT += tq[q];
+		}
+		__syncwarp();
+		const int one_t[1] = {nT};
+		good = zone_finish_seg<Zn64, 1, 4>(sm.tails, 0, one_t, gz, ZR_ZQ, zq, sm.zone, sm.cnt, lane,
+			rec.n, rec.nA, rec.nB, rec.nZL, rec.s1, rec.s2, rec.pivot, rec.A, rec.B, ZL, zscale, st);
+	}
+	if (lane == 0) {
+		if (good) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
+		else ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1132,10 +1818,11 @@ __device__ __forceinline__ double median_small(double* t, int m)
 	return (m & 1) ? t[m >> 1] : 0.5 * (t[(m >> 1) - 1] + t[m >> 1]);
 }
 
-// dynamic shared memory: three double arrays + the kd-tree of the IDW fill (index permutation, nodes)
+// dynamic shared memory: three double arrays + the kd-tree of the IDW fill (index permutation, nodes, build frontier)
 static size_t mesh_finalize_smem(int ntiles)
 {
-	return 3 * (size_t)ntiles * sizeof(double) + sizeof(uint16_t) * (size_t)((ntiles + 3) & ~3) + sizeof(KdtNode) * (size_t)(2 * ntiles + 2);
+	return 3 * (size_t)ntiles * sizeof(double) + sizeof(uint32_t) * (size_t)ntiles + sizeof(KdtNode) * (size_t)(2 * ntiles + 2)
+		+ sizeof(KdtFrontier) * 2 * (size_t)(2 * (ntiles / (KDT_LEAFSIZE + 1)) + 2);
 }
 
 __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
@@ -1188,10 +1875,12 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 	// The neighbour table of an FFI is kept with the good-mesh bitmap it belongs to; a later round whose bitmap is the
 	// same (the usual case) reuses it.
 	if (nexcl) {
-		uint16_t* kidx = reinterpret_cast<uint16_t*>(tmp + nt_tiles);
-		KdtNode* knodes = reinterpret_cast<KdtNode*>(kidx + ((nt_tiles + 3) & ~3));
+		uint32_t* kidx = reinterpret_cast<uint32_t*>(tmp + nt_tiles);
+		KdtNode* knodes = reinterpret_cast<KdtNode*>(kidx + nt_tiles);
+		KdtFrontier* kfront = reinterpret_cast<KdtFrontier*>(knodes + 2 * nt_tiles + 2);
+		const int kcap = 2 * (nt_tiles / (KDT_LEAFSIZE + 1)) + 2;
 		__shared__ KdtTree tree;
-		__shared__ int s_same, s_ovf;
+		__shared__ int s_same, s_ovf, s_cnt[2], s_wcount[32];
 		uint32_t* bits = ws.idw_bits + (size_t)b * ((P.ntiles + 31) / 32 + 1);   // [0] = valid flag, then the bitmap
 		uint16_t* tab = ws.idw_tab + (size_t)b * P.ntiles * KDT_K;
 		const int nwords = (nt_tiles + 31) / 32;
@@ -1205,15 +1894,24 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 		__syncthreads();
 		const bool reuse = s_same != 0;
 		if (!reuse) {
-			if (tid == 0) {
-				int n = 0;
-				for (int t = 0; t < nt_tiles; ++t) if (val[t] == val[t]) kidx[n++] = (uint16_t)t;
-				tree.idx = kidx; tree.nodes = knodes; tree.npts = n; tree.nx = nx;
-				int stack[3 * 64];
-				kdt_build(tree, stack, 2 * nt_tiles + 2);
-				if (tree.overflow) s_ovf = 1;
-				bits[0] = 1u;
+			// good meshes in increasing mesh id (the reference's point order), packed with their coordinates
+			int base = 0;
+			for (int t0 = 0; t0 < nt_tiles; t0 += nt) {
+				const int t = t0 + tid;
+				const bool g = t < nt_tiles && val[t] == val[t];
+				const unsigned bal = __ballot_sync(0xffffffffu, g);
+				if ((tid & 31) == 0) s_wcount[tid >> 5] = __popc(bal);
+				__syncthreads();
+				int off = base;
+				for (int w = 0; w < (tid >> 5); ++w) off += s_wcount[w];
+				if (g) kidx[off + __popc(bal & ((1u << (tid & 31)) - 1u))] = kdt_pack(t, nx);
+				for (int w = 0; w < (nt >> 5); ++w) base += s_wcount[w];
+				__syncthreads();
 			}
+			if (tid == 0) { tree.idx = kidx; tree.nodes = knodes; tree.npts = base; tree.nx = nx; bits[0] = 1u; }
+			__syncthreads();
+			kdt_build_cta(tree, kfront, kcap, 2 * nt_tiles + 2, s_cnt);
+			if (tid == 0 && tree.overflow) s_ovf = 1;
 			__syncthreads();
 		}
 		for (int t = tid; t < nt_tiles; t += nt) {
@@ -1449,7 +2147,7 @@ unsigned long long tbk_launch_counter(void) { return g_launches; }
 
 int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
 	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
-	tbk_ffi_status* status, cudaStream_t st, float* prof_ms, int tile_kernel)
+	tbk_ffi_status* status, cudaStream_t st, float* prof_ms, int tile_kernel, const TbkSide* side)
 {
 	FitProf* prof = nullptr;
 	FitProf pstore;
@@ -1460,10 +2158,22 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	}
 	const dim3 gt(P.ntiles, B);
 	const int gb = (B + 127) / 128;
+	bool base_forked = false;
 	LAUNCH(TBK_K_MISC, (k_init_ctl<<<gb, 128, 0, st>>>(P, ws, meta, B)));
 	if (tile_kernel == 0) LAUNCH(TBK_K_TILE_BASE, (k_tile_base<<<gt, TBK_NT, 0, st>>>(P, ws, cube, extra, mask)));
-	else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
-	else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 3 && extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<true, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
+	else {
+		const dim3 gz((P.ntiles + ZB_WARPS - 1) / ZB_WARPS, B);
+		if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
+		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
+		// the queued meshes (bucketed statistics) are only needed by k_mesh_finalize: side stream, joined before round 0's
+		cudaStream_t fs = st;
+		if (side && !prof) { fs = side->stream; cudaEventRecord(side->fork, st); cudaStreamWaitEvent(fs, side->fork, 0); base_forked = true; }
+		if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_fb<true><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
+		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_fb<false><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
+		if (base_forked) cudaEventRecord(side->join, fs);
+	}
 	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));
 	if (!launch_ok("base")) return TBK_ERR_CUDA;
 	const size_t mesh_smem = mesh_finalize_smem(P.ntiles);
@@ -1482,10 +2192,21 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 			else LAUNCH(TBK_K_RING_GATHER, (k_ring_gather_t<<<dim3(P.n_ringtiles, B), 256, 0, st>>>(P, ws, cube, mask, round)));
 			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
 			LAUNCH(TBK_K_RADIAL_FIT, (k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B)));
-			if (P.n_nonflat > 0)
+			if (P.n_nonflat > 0) {
 				if (tile_kernel == 0) LAUNCH(TBK_K_TILE_ROUND, (k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask)));
-				else LAUNCH(TBK_K_TILE_ROUND, (k_tile_round_w<<<dim3(P.n_nonflat, B), 128, 0, st>>>(P, ws, cube, mask)));
+				else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_ROUND, (k_tile_round_w<false><<<dim3(P.n_nonflat, B), 128, 0, st>>>(P, ws, cube, mask, round)));
+				else {
+					LAUNCH(TBK_K_TILE_ROUND, (k_tile_round_z<<<dim3(P.n_nonflat, B), 128, 0, st>>>(P, ws, cube, mask, round)));
+					LAUNCH(TBK_K_TILE_ROUND, (k_tile_round_fin<<<dim3((P.n_nonflat + ZF_WARPS - 1) / ZF_WARPS, B), 32 * ZF_WARPS, 0, st>>>(P, ws, round)));
+					// the queued meshes are only needed by this round's k_mesh_finalize: side stream, joined there
+					cudaStream_t fs = st;
+					if (side && !prof) { fs = side->stream; cudaEventRecord(side->fork, st); cudaStreamWaitEvent(fs, side->fork, 0); base_forked = true; }
+					LAUNCH(TBK_K_TILE_ROUND, (k_tile_round_w<true><<<296, 128, 0, fs>>>(P, ws, cube, mask, round)));
+					if (fs != st) cudaEventRecord(side->join, fs);
+				}
+			}
 		}
+		if (base_forked) { cudaStreamWaitEvent(st, side->join, 0); base_forked = false; }
 		LAUNCH(TBK_K_MESH, (k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round)));
 		if (!launch_ok("round")) return TBK_ERR_CUDA;
 	}

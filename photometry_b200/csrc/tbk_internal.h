@@ -8,11 +8,18 @@ struct Workspace;
 
 void tbk_set_error(const char* fmt, ...);
 
+// A side stream per caller stream: the fallback kernels of the zone statistics (a per cent of the meshes, latency bound) run
+// there, forked / joined with events, while the caller's stream goes on with kernels that do not need their results.
+struct TbkSide {
+	cudaStream_t stream;
+	cudaEvent_t fork, join;
+};
+
 // tbk_fit.cu
 int tbk_fit_configure(void);
 int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int B,
 	const tbk_ffi_meta* meta, const uint8_t* extra, float* bkg, uint8_t* mask,
-	tbk_ffi_status* status, cudaStream_t st, float* prof_ms, int tile_kernel);
+	tbk_ffi_status* status, cudaStream_t st, float* prof_ms, int tile_kernel, const TbkSide* side);
 unsigned long long tbk_launch_counter(void);
 
 // tbk_prepare.cu

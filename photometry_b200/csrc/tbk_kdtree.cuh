@@ -44,29 +44,30 @@ struct KdtNode {
 };
 
 struct KdtTree {
-	uint16_t* idx;       // [npts] permutation of the good mesh ids
+	uint32_t* idx;       // [npts] permutation of the good meshes, each packed as (iy << 22) | (ix << 12) | mesh id
 	KdtNode* nodes;      // [<= 2 npts]
 	int npts, nnodes, nx;
 	int mins[2], maxes[2];
 	int overflow;        // node array or build stack exhausted (never for npts <= 4096 with the sizes used here)
 };
 
-KDT_HD int kdt_coord(int g, int nx, int d) { return d == 0 ? g / nx : g % nx; }
+KDT_HD uint32_t kdt_pack(int g, int nx) { return ((uint32_t)(g / nx) << 22) | ((uint32_t)(g % nx) << 12) | (uint32_t)g; }
+KDT_HD int kdt_id(uint32_t w) { return (int)(w & 0xFFFu); }
 // order of the median selection: the coordinate along d alone (equal coordinates are equivalent -- where they end up
 // is decided by the selection algorithm, which is why it is restated step by step below)
-KDT_HD int kdt_key(int g, int nx, int d) { return kdt_coord(g, nx, d); }
+KDT_HD int kdt_key(uint32_t w, int d) { return d == 0 ? (int)(w >> 22) : (int)((w >> 12) & 0x3FFu); }
 
 // ---- selection: after the call p[nth] is the element of rank nth, smaller keys before it, larger after it -------
-KDT_HD void kdt_swap(uint16_t& x, uint16_t& y) { const uint16_t t = x; x = y; y = t; }
+KDT_HD void kdt_swap(uint32_t& x, uint32_t& y) { const uint32_t t = x; x = y; y = t; }
 
-KDT_HD void kdt_sift_down(uint16_t* p, int hole, int len, uint16_t value, int nx, int d)
+KDT_HD void kdt_sift_down(uint32_t* p, int hole, int len, uint32_t value, int d)
 {
 	// max-heap on the key: move the hole down along the larger child, then bubble the value up from there
 	const int top = hole;
 	int child = hole;
 	while (child < (len - 1) / 2) {
 		child = 2 * (child + 1);
-		if (kdt_key(p[child], nx, d) < kdt_key(p[child - 1], nx, d)) --child;
+		if (kdt_key(p[child], d) < kdt_key(p[child - 1], d)) --child;
 		p[hole] = p[child];
 		hole = child;
 	}
@@ -76,7 +77,7 @@ KDT_HD void kdt_sift_down(uint16_t* p, int hole, int len, uint16_t value, int nx
 		hole = child - 1;
 	}
 	int parent = (hole - 1) / 2;
-	while (hole > top && kdt_key(p[parent], nx, d) < kdt_key(value, nx, d)) {
+	while (hole > top && kdt_key(p[parent], d) < kdt_key(value, d)) {
 		p[hole] = p[parent];
 		hole = parent;
 		parent = (hole - 1) / 2;
@@ -84,25 +85,25 @@ KDT_HD void kdt_sift_down(uint16_t* p, int hole, int len, uint16_t value, int nx
 	p[hole] = value;
 }
 
-KDT_HD void kdt_heap_select(uint16_t* p, int middle, int last, int nx, int d)
+KDT_HD void kdt_heap_select(uint32_t* p, int middle, int last, int d)
 {
 	// heap of the `middle` smallest at the front
 	if (middle >= 2) {
 		for (int parent = (middle - 2) / 2; ; --parent) {
-			kdt_sift_down(p, parent, middle, p[parent], nx, d);
+			kdt_sift_down(p, parent, middle, p[parent], d);
 			if (parent == 0) break;
 		}
 	}
 	for (int i = middle; i < last; ++i) {
-		if (kdt_key(p[i], nx, d) < kdt_key(p[0], nx, d)) {
-			const uint16_t v = p[i];
+		if (kdt_key(p[i], d) < kdt_key(p[0], d)) {
+			const uint32_t v = p[i];
 			p[i] = p[0];
-			kdt_sift_down(p, 0, middle, v, nx, d);
+			kdt_sift_down(p, 0, middle, v, d);
 		}
 	}
 }
 
-KDT_HD void kdt_nth_element(uint16_t* p, int nth, int n, int nx, int d)
+KDT_HD void kdt_nth_element(uint32_t* p, int nth, int n, int d)
 {
 	if (n == 0 || nth == n) return;
 	int first = 0, last = n;
@@ -111,7 +112,7 @@ KDT_HD void kdt_nth_element(uint16_t* p, int nth, int n, int nx, int d)
 	depth *= 2;
 	while (last - first > 3) {
 		if (depth == 0) {
-			kdt_heap_select(p + first, nth + 1 - first, last - first, nx, d);
+			kdt_heap_select(p + first, nth + 1 - first, last - first, d);
 			kdt_swap(p[first], p[nth]);
 			return;
 		}
@@ -120,18 +121,18 @@ KDT_HD void kdt_nth_element(uint16_t* p, int nth, int n, int nx, int d)
 		const int mid = first + (last - first) / 2;
 		{
 			const int a = first + 1, b = mid, c = last - 1;
-			const int ka = kdt_key(p[a], nx, d), kb = kdt_key(p[b], nx, d), kc = kdt_key(p[c], nx, d);
+			const int ka = kdt_key(p[a], d), kb = kdt_key(p[b], d), kc = kdt_key(p[c], d);
 			int m3;
 			if (ka < kb) m3 = (kb < kc) ? b : ((ka < kc) ? c : a);
 			else m3 = (ka < kc) ? a : ((kb < kc) ? c : b);
 			kdt_swap(p[first], p[m3]);
 		}
-		const int kp = kdt_key(p[first], nx, d);
+		const int kp = kdt_key(p[first], d);
 		int lo = first + 1, hi = last;
 		for (;;) {
-			while (kdt_key(p[lo], nx, d) < kp) ++lo;
+			while (kdt_key(p[lo], d) < kp) ++lo;
 			--hi;
-			while (kp < kdt_key(p[hi], nx, d)) --hi;
+			while (kp < kdt_key(p[hi], d)) --hi;
 			if (!(lo < hi)) break;
 			kdt_swap(p[lo], p[hi]);
 			++lo;
@@ -140,31 +141,87 @@ KDT_HD void kdt_nth_element(uint16_t* p, int nth, int n, int nx, int d)
 	}
 	// insertion sort of the last <= 3 elements
 	for (int i = first + 1; i < last; ++i) {
-		const uint16_t v = p[i];
-		const int kv = kdt_key(v, nx, d);
+		const uint32_t v = p[i];
+		const int kv = kdt_key(v, d);
 		int j = i;
-		while (j > first && kv < kdt_key(p[j - 1], nx, d)) { p[j] = p[j - 1]; --j; }
+		while (j > first && kv < kdt_key(p[j - 1], d)) { p[j] = p[j - 1]; --j; }
 		p[j] = v;
 	}
 }
 
-// ---- build (one thread) ---------------------------------------------------------------------------------
-// `stack` is scratch of at least 3 * 64 ints.  Returns the number of nodes; node 0 is the root.
-KDT_HD void kdt_build(KdtTree& t, int* stack, int max_nodes)
+// ---- build --------------------------------------------------------------------------------------------------
+// One node: points idx[s .. e).  Returns false for a leaf; otherwise rearranges the points and returns the split
+// dimension / value and the position p of the first point of the ">= split" side.
+KDT_HD bool kdt_split(uint32_t* idx, int s, int e, int& p, int& dim, int& split)
 {
-	const int nx = t.nx;
-	uint16_t* idx = t.idx;
-	t.nnodes = 0; t.overflow = 0;
+	if (e - s <= KDT_LEAFSIZE) return false;
+	int mn[2] = {KDT_INF, KDT_INF}, mx[2] = {-1, -1};
+	for (int i = s; i < e; ++i) {
+		const uint32_t w = idx[i];
+		const int c0 = kdt_key(w, 0), c1 = kdt_key(w, 1);
+		if (c0 < mn[0]) mn[0] = c0;
+		if (c0 > mx[0]) mx[0] = c0;
+		if (c1 < mn[1]) mn[1] = c1;
+		if (c1 > mx[1]) mx[1] = c1;
+	}
+	int d = 0, size = 0;
+	for (int i = 0; i < 2; ++i) if (mx[i] - mn[i] > size) { d = i; size = mx[i] - mn[i]; }
+	if (mx[d] == mn[d]) return false;   // all points identical (cannot happen on a lattice)
+	const int n = e - s;
+	kdt_nth_element(idx + s, n / 2, n, d);
+	split = kdt_key(idx[s + n / 2], d);
+	p = s;
+	int q = e - 1;
+	while (p <= q) {
+		if (kdt_key(idx[p], d) < split) ++p;
+		else if (kdt_key(idx[q], d) >= split) --q;
+		else { kdt_swap(idx[p], idx[q]); ++p; --q; }
+	}
+	if (p == s) {
+		// no point below the split: the smallest coordinate becomes the split and goes left alone
+		int j = s;
+		split = kdt_key(idx[j], d);
+		for (int i = s + 1; i < e; ++i) {
+			const int c = kdt_key(idx[i], d);
+			if (c < split) { j = i; split = c; }
+		}
+		kdt_swap(idx[s], idx[j]);
+		p = s + 1;
+	} else if (p == e) {
+		int j = e - 1;
+		split = kdt_key(idx[j], d);
+		for (int i = s; i < e - 1; ++i) {
+			const int c = kdt_key(idx[i], d);
+			if (c > split) { j = i; split = c; }
+		}
+		kdt_swap(idx[e - 1], idx[j]);
+		p = e - 1;
+	}
+	dim = d;
+	return true;
+}
+
+// bounding box of all points (the tree's mins / maxes, which seed the cell distances of a search)
+KDT_HD void kdt_root_box(KdtTree& t)
+{
 	for (int d = 0; d < 2; ++d) { t.mins[d] = KDT_INF; t.maxes[d] = -1; }
 	for (int i = 0; i < t.npts; ++i)
 		for (int d = 0; d < 2; ++d) {
-			const int c = kdt_coord(idx[i], nx, d);
+			const int c = kdt_key(t.idx[i], d);
 			if (c < t.mins[d]) t.mins[d] = c;
 			if (c > t.maxes[d]) t.maxes[d] = c;
 		}
+}
+
+// Serial build (host tests).  `stack` is scratch of at least 3 * 64 ints; node 0 is the root.
+KDT_HD void kdt_build(KdtTree& t, int* stack, int max_nodes)
+{
+	uint32_t* idx = t.idx;
+	t.nnodes = 0; t.overflow = 0;
+	kdt_root_box(t);
 	if (t.npts == 0) return;
 	int sp = 0;
-	// entry: (start, end, (parent << 1) | side), parent -1 for the root
+	// entry: (start, end, (parent << 1) | side), -2 for the root
 	stack[0] = 0; stack[1] = t.npts; stack[2] = -2; sp = 1;
 	while (sp > 0) {
 		--sp;
@@ -174,55 +231,62 @@ KDT_HD void kdt_build(KdtTree& t, int* stack, int max_nodes)
 		if (link >= 0) { if (link & 1) t.nodes[link >> 1].b = (uint16_t)me; else t.nodes[link >> 1].a = (uint16_t)me; }
 		KdtNode nd;
 		nd.a = (uint16_t)s; nd.b = (uint16_t)e; nd.split = 0; nd.dim = -1;
-		if (e - s > KDT_LEAFSIZE) {
-			int mn[2] = {KDT_INF, KDT_INF}, mx[2] = {-1, -1};
-			for (int i = s; i < e; ++i)
-				for (int d = 0; d < 2; ++d) {
-					const int c = kdt_coord(idx[i], nx, d);
-					if (c < mn[d]) mn[d] = c;
-					if (c > mx[d]) mx[d] = c;
-				}
-			int d = 0, size = 0;
-			for (int i = 0; i < 2; ++i) if (mx[i] - mn[i] > size) { d = i; size = mx[i] - mn[i]; }
-			if (mx[d] != mn[d]) {
-				const int n = e - s;
-				kdt_nth_element(idx + s, n / 2, n, nx, d);
-				int split = kdt_coord(idx[s + n / 2], nx, d);
-				int p = s, q = e - 1;
-				while (p <= q) {
-					if (kdt_coord(idx[p], nx, d) < split) ++p;
-					else if (kdt_coord(idx[q], nx, d) >= split) --q;
-					else { kdt_swap(idx[p], idx[q]); ++p; --q; }
-				}
-				if (p == s) {
-					// no point below the split: the smallest coordinate becomes the split and goes left alone
-					int j = s;
-					split = kdt_coord(idx[j], nx, d);
-					for (int i = s + 1; i < e; ++i) {
-						const int c = kdt_coord(idx[i], nx, d);
-						if (c < split) { j = i; split = c; }
-					}
-					kdt_swap(idx[s], idx[j]);
-					p = s + 1;
-				} else if (p == e) {
-					int j = e - 1;
-					split = kdt_coord(idx[j], nx, d);
-					for (int i = s; i < e - 1; ++i) {
-						const int c = kdt_coord(idx[i], nx, d);
-						if (c > split) { j = i; split = c; }
-					}
-					kdt_swap(idx[e - 1], idx[j]);
-					p = e - 1;
-				}
-				nd.dim = (int16_t)d; nd.split = (int16_t)split;
-				if (sp + 2 > 64) { t.overflow = 1; return; }
-				stack[3 * sp] = p; stack[3 * sp + 1] = e; stack[3 * sp + 2] = (me << 1) | 1; ++sp;
-				stack[3 * sp] = s; stack[3 * sp + 1] = p; stack[3 * sp + 2] = (me << 1); ++sp;
-			}
+		int p, dim, split;
+		if (kdt_split(idx, s, e, p, dim, split)) {
+			nd.dim = (int16_t)dim; nd.split = (int16_t)split;
+			if (sp + 2 > 64) { t.overflow = 1; return; }
+			stack[3 * sp] = p; stack[3 * sp + 1] = e; stack[3 * sp + 2] = (me << 1) | 1; ++sp;
+			stack[3 * sp] = s; stack[3 * sp + 1] = p; stack[3 * sp + 2] = (me << 1); ++sp;
 		}
 		t.nodes[me] = nd;
 	}
 }
+
+#ifdef __CUDACC__
+// Level-parallel build by one CTA: the nodes of a level are independent, so thread i splits frontier entry i; the
+// arrangement inside every node is the serial one.  `frontier` is scratch of 2 * cap entries of 3 uint16, cap >=
+// 2 * (npts / (KDT_LEAFSIZE + 1)) + 2.  t.idx / t.npts / t.nx are set by the caller (idx filled), all threads call.
+struct KdtFrontier { uint16_t s, e, node; };
+__device__ __forceinline__ void kdt_build_cta(KdtTree& t, KdtFrontier* frontier, int cap, int max_nodes, int* s_cnt /* [2] shared */)
+{
+	const int tid = threadIdx.x, nt = blockDim.x;
+	if (tid == 0) {
+		t.overflow = 0; t.nnodes = t.npts > 0 ? 1 : 0;
+		kdt_root_box(t);
+		frontier[0].s = 0; frontier[0].e = (uint16_t)t.npts; frontier[0].node = 0;
+		s_cnt[0] = t.npts > 0 ? 1 : 0; s_cnt[1] = 0;
+	}
+	__syncthreads();
+	int cur = 0;
+	for (int level = 0; level < 4096; ++level) {
+		const int nfr = s_cnt[cur];
+		if (nfr == 0) break;
+		KdtFrontier* fc = frontier + cur * cap;
+		KdtFrontier* fn = frontier + (cur ^ 1) * cap;
+		for (int i = tid; i < nfr; i += nt) {
+			const int s = fc[i].s, e = fc[i].e, me = fc[i].node;
+			KdtNode nd;
+			nd.a = (uint16_t)s; nd.b = (uint16_t)e; nd.split = 0; nd.dim = -1;
+			int p, dim, split;
+			if (kdt_split(t.idx, s, e, p, dim, split)) {
+				const int a = atomicAdd(&t.nnodes, 2);
+				const int j = atomicAdd(&s_cnt[cur ^ 1], 2);
+				if (a + 2 > max_nodes || j + 2 > cap) t.overflow = 1;
+				else {
+					nd.a = (uint16_t)a; nd.b = (uint16_t)(a + 1); nd.dim = (int16_t)dim; nd.split = (int16_t)split;
+					fn[j].s = (uint16_t)s; fn[j].e = (uint16_t)p; fn[j].node = (uint16_t)a;
+					fn[j + 1].s = (uint16_t)p; fn[j + 1].e = (uint16_t)e; fn[j + 1].node = (uint16_t)(a + 1);
+				}
+			}
+			t.nodes[me] = nd;
+		}
+		__syncthreads();
+		if (tid == 0) { s_cnt[cur] = 0; if (t.overflow) s_cnt[cur ^ 1] = 0; }
+		cur ^= 1;
+		__syncthreads();
+	}
+}
+#endif
 
 // ---- query --------------------------------------------------------------------------------------------------
 struct KdtCell { int dist, sd0, sd1, node; };
@@ -261,7 +325,6 @@ KDT_HD int kdt_query(const KdtTree& t, int qy, int qx, int kmax, int* out_id, in
 	KdtNb nb[KDT_K];
 	int nq = 0, nn = 0;
 	if (t.npts == 0) return 0;
-	const int nx = t.nx;
 	const int x[2] = {qy, qx};
 	KdtCell cur;
 	{
@@ -278,8 +341,9 @@ KDT_HD int kdt_query(const KdtTree& t, int qy, int qx, int kmax, int* out_id, in
 		const KdtNode nd = t.nodes[cur.node];
 		if (nd.dim < 0) {
 			for (int i = nd.a; i < nd.b; ++i) {
-				const int g = t.idx[i];
-				const int dy = g / nx - qy, dx = g % nx - qx;
+				const uint32_t w = t.idx[i];
+				const int g = kdt_id(w);
+				const int dy = kdt_key(w, 0) - qy, dx = kdt_key(w, 1) - qx;
 				const int d2 = dy * dy + dx * dx;
 				if (d2 < upper) {
 					if (nn == kmax) kdt_heap_remove(nb, nn);

@@ -8,6 +8,7 @@ goes to the device through a pinned staging buffer and ``tbk_decode_ffi_be`` byt
 ``[0:2048, 44:2092]`` straight into the cube.
 """
 import ctypes as C
+from collections import deque
 from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
@@ -25,15 +26,24 @@ def decode_ffi_be(raw_dev, B, naxis1, naxis2, out, row0=0, col0=44):
 	return out
 
 
+def _read_hdu(path):
+	"""Worker: inflate + parse one file; only the image HDU's own bytes are kept (not the whole inflated file)."""
+	hdr, raw, n1, n2 = read_ffi_raw(path)
+	return hdr, np.frombuffer(raw, dtype=np.uint8).copy(), n1, n2
+
+
 def load_ffi_stack(paths, device=None, threads=8, batch=8):
 	"""
 	Read the FFIs in ``paths`` (time ordered) into a CUDA tensor float32 [N, 2048, 2048].
 	Returns ``(cube, headers)``; ``photometry_b200.meta_from_headers(headers)`` gives the per-FFI meta.
+	At most ``2 * batch`` decoded files (17.7 MB each) are held on the host at any time.
 	"""
 	if not torch.cuda.is_available():
 		raise _lib.TbkError("CUDA device required: photometry_b200 has no CPU fallback")
 	device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 	n = len(paths)
+	if n == 0:
+		raise ValueError("load_ffi_stack: no files given")
 	H = W = 2048
 	cube = torch.empty((n, H, W), dtype=torch.float32, device=device)
 	headers = [None] * n
@@ -42,18 +52,28 @@ def load_ffi_stack(paths, device=None, threads=8, batch=8):
 	stage_dev = [torch.empty((batch, hdu_bytes), dtype=torch.uint8, device=device) for _ in range(2)]
 	done = [torch.cuda.Event(), torch.cuda.Event()]
 	with ThreadPoolExecutor(max_workers=threads) as pool:
-		it = pool.map(read_ffi_raw, paths)
+		# a bounded window of reads in flight, consumed in file order
+		pending = deque()
+		submitted = 0
+
+		def refill():
+			nonlocal submitted
+			while submitted < n and len(pending) < 2 * batch:
+				pending.append(pool.submit(_read_hdu, paths[submitted]))
+				submitted += 1
+		refill()
 		for bi, a in enumerate(range(0, n, batch)):
 			b = min(a + batch, n)
 			k = bi & 1
 			if bi >= 2:
 				done[k].synchronize()   # the staging buffer must have been consumed
 			for j in range(a, b):
-				hdr, raw, n1, n2 = next(it)
+				hdr, raw, n1, n2 = pending.popleft().result()
+				refill()
 				if (n1, n2) != (2136, 2078):
 					raise ValueError(f"{paths[j]}: unexpected image size {n1} x {n2}")
 				headers[j] = hdr
-				stage[k].numpy()[j - a, :] = np.frombuffer(raw, dtype=np.uint8)
+				stage[k].numpy()[j - a, :] = raw
 			stage_dev[k][:b - a].copy_(stage[k][:b - a], non_blocking=True)
 			decode_ffi_be(stage_dev[k], b - a, 2136, 2078, cube[a:b])
 			done[k].record()

@@ -75,6 +75,20 @@ class SectorResult:
 	numfiles: int                         # global number of cadences
 
 
+def check_status(status, first_cadence=0):
+	"""
+	The reference aborts when a frame has no usable mesh: photutils raises ``ValueError`` from ``Background2D`` (every
+	mesh has more than ``exclude_percentile`` masked pixels) and ``prepare_photometry`` lets it propagate.  The batched
+	kernels report that condition per FFI in ``tbk_ffi_status.no_good_mesh`` and write a NaN background; this raises the
+	same exception type, naming the cadences, so that such a frame can never be smoothed over or accumulated silently.
+	"""
+	bad = np.flatnonzero(np.asarray(status['no_good_mesh']) != 0)
+	if bad.size:
+		raise ValueError("All meshes contain > 2048 (50.0 percent per mesh) masked pixels in cadence(s) %s of this stack: "
+			"fit_background cannot estimate a background (photutils.Background2D raises here in the reference)"
+			% ', '.join(str(int(first_cadence + k)) for k in bad[:20]) + (' ...' if bad.size > 20 else ''))
+
+
 def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, keep_images=True,
 	backgrounds_pixels_threshold=0.5, group=None):
 	"""
@@ -114,8 +128,9 @@ def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, k
 	sumimage = pixels_used = None
 	if is_root:
 		sumimage, pixels_used = fitter.sum_finalize(sum_, nimg, used, numfiles, backgrounds_pixels_threshold)
-	return SectorResult(bkg_us, bkg, flags, images, sumimage, pixels_used, nimg, used,
-		status.cpu().numpy().view(STATUS_DTYPE), numfiles)
+	status_np = status.cpu().numpy().view(STATUS_DTYPE)
+	check_status(status_np)
+	return SectorResult(bkg_us, bkg, flags, images, sumimage, pixels_used, nimg, used, status_np, numfiles)
 
 
 def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3, extra_mask=None):
@@ -125,10 +140,13 @@ def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3,
 	``nbuf`` device staging buffers and three streams (H2D, compute, D2H).
 
 	host_cube  float32 pinned CPU tensor [n, H, W];  out_bkg float32 / out_mask uint8 pinned CPU tensors
-	Returns the number of bytes copied (h2d, d2h).
+	Returns the number of bytes copied (h2d, d2h).  Raises ``ValueError`` (like the reference) when a frame has no usable mesh.
 	"""
+	from ._lib import STATUS_DTYPE
 	n, H, W = host_cube.shape
 	dev = fitter.device
+	ssz = STATUS_DTYPE.itemsize
+	status = torch.empty(n * ssz, dtype=torch.uint8, device=dev)
 	meta_d = fitter.meta_to_device(np.ascontiguousarray(meta))
 	isz = meta.dtype.itemsize
 	s_in, s_c, s_out = (torch.cuda.Stream(dev) for _ in range(3))
@@ -153,7 +171,8 @@ def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3,
 			ev_in[k].record(s_in)
 		s_c.wait_event(ev_in[k])
 		with torch.cuda.stream(s_c):
-			fitter.fit(ins[k][:m], meta_d[a * isz:b * isz], bkg_out=bks[k][:m], mask_out=mks[k][:m])
+			fitter.fit(ins[k][:m], meta_d[a * isz:b * isz], None if extra_mask is None else extra_mask[a:b].to(dev, non_blocking=True),
+				bkg_out=bks[k][:m], mask_out=mks[k][:m], status_out=status[a * ssz:b * ssz])
 			ev_c[k].record(s_c)
 		s_out.wait_event(ev_c[k])
 		with torch.cuda.stream(s_out):
@@ -162,4 +181,5 @@ def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3,
 			ev_out[k].record(s_out)
 	for s in (s_in, s_c, s_out):
 		cur.wait_stream(s)
+	check_status(status.cpu().numpy().view(STATUS_DTYPE))   # synchronises: the results are complete on return
 	return n * H * W * 4, n * H * W * 5
