@@ -205,12 +205,15 @@ __device__ __forceinline__ RadialTab radial_tab(const double* rtab_b, const FfiC
 	t.nsub = TBK_RSUB * max(P.nrings - 1, 1); t.radial_ok = c.radial_ok;
 	return t;
 }
-// the same evaluation from rows [jlo, jlo + nrows) staged in shared memory (r must map into that range)
+// the same evaluation from rows [jlo, jlo + nrows) staged in shared memory (r must map into that range).  The staged rows
+// are TBK_RROW = 10 doubles apart: with the natural stride of 8 (64 B) the lanes of a quarter warp, which read the same
+// coefficient of DIFFERENT rows, would fall on two 16-byte bank groups only (4-way conflicts); 80 B spreads them over all eight.
+#define TBK_RROW 10
 __device__ __forceinline__ double radial_tab_eval_s(const RadialTab& t, const double* srows, int jlo, double r)
 {
 	const double tc = clamp_d(r, t.x0, t.xlast);
 	const int j = max(0, min(t.nsub - 1, (int)((tc - t.center0) * t.inv_h))) - jlo;
-	const double2* row = reinterpret_cast<const double2*>(srows + 8 * j);
+	const double2* row = reinterpret_cast<const double2*>(srows + TBK_RROW * j);
 	const double2 c01 = row[0], c23 = row[1], c45 = row[2], c6u = row[3];
 	const double u = tc - c6u.y;
 	return fma(u, fma(u, fma(u, fma(u, fma(u, fma(u, c6u.x, c45.y), c45.x), c23.y), c23.x), c01.y), c01.x);

@@ -1111,6 +1111,7 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 	//   packed (default): two 32-bit atomics per sample -- word A = count (8 bit) | sum of the top 16 bits of rem (24 bit),
 	//     word B = sum of the next 24 bits of rem; exact to 2^-40 per sample as long as no cell holds more than 255
 	//     samples, which is verified afterwards (the count fields must add up to the number of binned samples);
+	//   long rings (n > 8192): three atomics -- count, two 20-bit halves of the fraction -- good up to 4095 samples per cell;
 	//   fixed: four atomics per sample (count + 48-bit fraction in three 16-bit chunks), exact for n < 65536;
 	//   otherwise float64 CAS adds.
 	uint32_t* lb = reinterpret_cast<uint32_t*>(sm.x);   // [4][TBK_KDE_M] overlay on the FFT buffer
@@ -1127,7 +1128,7 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 		return li > 1 && li < TBK_KDE_M - 1;
 	};
 	bool packed = false;
-	{
+	if (n <= 8192) {
 		for (int i = tid; i < 2 * TBK_KDE_M; i += nt) lb[i] = 0u;
 		__syncthreads();
 		int nb = 0;
@@ -1159,6 +1160,42 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 				double Sm = 0.0;
 				if (cidx > 0) Sm = (double)(lb[cidx - 1] & 0xFFFFFFu) * 1.52587890625e-05 + (double)lb[TBK_KDE_M + cidx - 1] * 9.094947017729282e-13;
 				g[j] = ((double)(A >> 24) - S) + Sm;
+			}
+			__syncthreads();
+			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
+			__syncthreads();
+		}
+	} else {
+		// long rings: three atomics per sample -- count, and the fraction as two 20-bit halves (exact to 2^-40 per sample
+		// as long as no cell holds more than 4095 samples, verified afterwards)
+		for (int i = tid; i < 3 * TBK_KDE_M; i += nt) lb[i] = 0u;
+		__syncthreads();
+		each([&](double d) {
+			int li; double rem;
+			if (cell_of(d, li, rem)) {
+				const double t = rem * 1048576.0;
+				const unsigned h20 = (unsigned)t;
+				const unsigned l20 = (unsigned)((t - (double)h20) * 1048576.0);
+				atomicAdd(&lb[li], 1u);
+				atomicAdd(&lb[TBK_KDE_M + li], h20);
+				atomicAdd(&lb[2 * TBK_KDE_M + li], l20);
+			}
+		});
+		__syncthreads();
+		int cmax = 0;
+		for (int j = tid; j < TBK_KDE_M; j += nt) cmax = max(cmax, (int)lb[j]);
+		double zmn = 0.0, zmx = (double)cmax;
+		int zi = 0;
+		block_sum_min_max(sm.red, zi, zmn, zmx);
+		packed = zmx <= 4095.0;
+		if (packed) {
+			double g[TBK_KDE_M / TBK_KDE_NT];
+			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) {
+				const int cidx = tid + j * nt;
+				const double S = (double)lb[TBK_KDE_M + cidx] * 9.5367431640625e-07 + (double)lb[2 * TBK_KDE_M + cidx] * 9.094947017729282e-13;
+				double Sm = 0.0;
+				if (cidx > 0) Sm = (double)lb[TBK_KDE_M + cidx - 1] * 9.5367431640625e-07 + (double)lb[2 * TBK_KDE_M + cidx - 1] * 9.094947017729282e-13;
+				g[j] = ((double)lb[cidx] - S) + Sm;
 			}
 			__syncthreads();
 			for (int j = 0; j < TBK_KDE_M / TBK_KDE_NT; ++j) sm.x[tid + j * nt] = make_double2(g[j], 0.0);
@@ -1577,7 +1614,7 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 #define ZR_ROWS 56
 struct ZoneRoundSmem {
 	double d[TBK_NPIX_TILE];          // staged residuals, NaN = masked
-	double rows[ZR_ROWS][8];          // the Taylor pieces this mesh can see (RadialTab rows jlo .. jlo + ZR_ROWS - 1)
+	double rows[ZR_ROWS][TBK_RROW];   // the Taylor pieces this mesh can see (RadialTab rows jlo .. jlo + ZR_ROWS - 1), padded
 	unsigned long long bar;           // mbarrier of the TMA copy of the mesh's radius tile
 	double red[4][2];
 	int redi[4][4];
@@ -1628,7 +1665,7 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 			return;
 		}
 		for (int e = tid; e < (jhi - jlo + 1) * 4; e += 128)
-			reinterpret_cast<double2*>(&sm.rows[0][0])[e] = __ldg(reinterpret_cast<const double2*>(rt.rows + 8 * (size_t)jlo) + e);
+			reinterpret_cast<double2*>(&sm.rows[e >> 2][0])[e & 3] = __ldg(reinterpret_cast<const double2*>(rt.rows + 8 * (size_t)jlo) + e);
 	}
 	__syncthreads();                 // rows staged, barrier initialised
 	tma_bar_wait(&sm.bar, 0u);       // radius tile landed
