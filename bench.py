@@ -34,6 +34,21 @@ CAMERA, CCD = 1, 2
 SEED = 20260117 + 1
 
 
+def reference_probe():
+	"""
+	Can the real reference (tasoc/photometry) run here?  It needs astropy, photutils, statsmodels, bottleneck, h5py and its own
+	package on sys.path (PHOTOMETRY_REFERENCE, default /root/reference); the GPU box has no /root/reference, so this normally
+	reports False with the missing module list and the CPU arm times the oracle restatement (kind "port").
+	"""
+	import importlib.util
+	missing = [m for m in ('astropy', 'photutils', 'statsmodels', 'bottleneck', 'h5py', 'scipy') if importlib.util.find_spec(m) is None]
+	ref_dir = os.environ.get('PHOTOMETRY_REFERENCE', '/root/reference')
+	have_pkg = os.path.isdir(os.path.join(ref_dir, 'photometry'))
+	if not have_pkg:
+		missing.append('photometry (reference package)')
+	return {"reference_importable": not missing, "missing": missing}
+
+
 def load_peaks():
 	path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
 	if os.path.exists(path):
@@ -155,10 +170,88 @@ def run_reference(args):
 		"e2e": {"value": value, "unit": "FFIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}
+	line.update(reference_probe())
 	print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
+def sharded_parity(fit_cls, dev, world, rank, dist):
+	"""
+	Sharded-vs-single check carried in the bench line: a small replicated stack (24 cadences of 512 x 512) is run through
+	prepare_stack on every rank's cadence shard (halo exchange + packed reduce) and, on rank 0, through the same kernels
+	unsharded.  Returns booleans (rank 0) for time_smooth 9 and 27.
+	"""
+	import numpy as np
+	import torch
+	import photometry_b200 as pb
+	from photometry_b200 import synth
+	from photometry_b200.prepare import shard_bounds
+	n, Hs, Ws = 8 * max(world, 4), 512, 512
+	xycen = (-30.0, 560.0)
+	stack = synth.synth_stack_numpy(n, Hs, Ws, seed=77, xycen=xycen, radial_cutoff=500.0, n_stars=600)
+	hdrs = [dict(CAMERA=1, CCD=2, TSTART=1400.0 + 0.02 * k, TSTOP=1400.02 + 0.02 * k, FFIINDEX=9000 + k, DQUALITY=(32 if k % 5 == 2 else 0)) for k in range(n)]
+	meta = pb.meta_from_headers(hdrs)
+	fit = fit_cls((Hs, Ws), True, 1, 2, radial_cutoff=500, xycen=xycen, device=dev.index)
+	out = {}
+	for ts in (9, 27):
+		if n // world < ts // 2:
+			continue
+		lo, hi = shard_bounds(n, world, rank)
+		res = pb.prepare_stack(fit, torch.from_numpy(stack[lo:hi]).to(dev), meta[lo:hi], time_smooth=ts, chunk=8)
+		parts = [torch.empty((shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0], Hs, Ws), dtype=torch.float32, device=dev) for r in range(world)]
+		dist.all_gather(parts, res.backgrounds.contiguous())
+		if rank == 0:
+			cube = torch.from_numpy(stack).to(dev)
+			bk, mk, st = fit.fit(cube, meta)
+			sm = fit.time_smooth(bk, ts // 2)
+			s = torch.zeros((Hs, Ws), dtype=torch.float64, device=dev); ni = torch.zeros((Hs, Ws), dtype=torch.int32, device=dev); us = torch.zeros_like(ni)
+			fit.sum_accumulate(cube, sm, mk.clone(), meta, s, ni, us)
+			sumimage, used = fit.sum_finalize(s, ni, us, n, 0.5)
+			out[f"time_smooth_{ts}"] = {
+				"backgrounds_bit_equal": bool(torch.equal(torch.cat(parts), sm)),
+				"nimg_used_exact": bool(torch.equal(res.nimg, ni) and torch.equal(res.used, us) and torch.equal(res.backgrounds_pixels_used, used)),
+				"sumimage_rtol_1e-12": bool(torch.allclose(res.sumimage, sumimage, rtol=1e-12, equal_nan=True)),
+				"numfiles": int(res.numfiles)}
+	return out
+
+
+def sector_path(pb, synth, dist, dev, rank, world, total_ffis, time_smooth, camera, ccd, seed, chunk, streams, barrier, label):
+	"""
+	One synthetic sector of ``total_ffis`` cadences sharded contiguously over the ranks (strong scaling): fit + halo exchange
+	(w = time_smooth // 2) + time smoothing + sumimage accumulation + packed NCCL reduce + finalize.  Returns the dict for the
+	bench line (rank 0) -- FFIs/s over the max-over-ranks device time, and the halo / reduce milliseconds.
+	"""
+	import torch
+	from photometry_b200.prepare import shard_bounds
+	lo, hi = shard_bounds(total_ffis, world, rank)
+	n_loc = hi - lo
+	cube = synth.synth_stack_torch(n_loc, H, W, dev, camera=camera, ccd=ccd, seed=seed + rank)
+	hdrs = [dict(CAMERA=camera, CCD=ccd, TSTART=1400.0 + k * 600 / 86400, TSTOP=1400.0 + (k + 1) * 600 / 86400,
+		FFIINDEX=20000 + k, DQUALITY=(32 if k % 37 == 5 else 0)) for k in range(lo, hi)]
+	meta = pb.meta_from_headers(hdrs)
+	fit = pb.BackgroundFitter((H, W), True, camera, ccd, device=dev.index)
+	tm = {}
+	pb.prepare_stack(fit, cube[:min(n_loc, 2 * chunk)], meta[:min(n_loc, 2 * chunk)], time_smooth=time_smooth, chunk=chunk, keep_images=False, nstreams=streams)
+	barrier()
+	g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	g0.record()
+	res = pb.prepare_stack(fit, cube, meta, time_smooth=time_smooth, chunk=chunk, keep_images=False, timings=tm, nstreams=streams)
+	g1.record()
+	barrier()
+	ms = g0.elapsed_time(g1)
+	t = torch.tensor([ms, tm.get('halo_ms', 0.0), tm.get('reduce_ms', 0.0)], dtype=torch.float64, device=dev)
+	if world > 1:
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+	ms, halo_ms, reduce_ms = (float(x) for x in t.tolist())
+	out = {"value": total_ffis / (ms * 1e-3), "unit": "FFIs/s", "scaling": "strong", "total_ffis": total_ffis, "ffis_per_gpu": n_loc,
+		"time_smooth": time_smooth, "halo_w": time_smooth // 2, "ms": ms, "halo_ms": halo_ms, "reduce_ms": reduce_ms,
+		"limits": "fit kernels" if max(halo_ms, reduce_ms) < 0.1 * ms else ("halo exchange" if halo_ms > reduce_ms else "reduce"),
+		"numfiles": int(res.numfiles), "workload": label}
+	del res, cube
+	torch.cuda.empty_cache()
+	return out
+
+
 def run_b200(args):
 	import numpy as np
 	import torch
@@ -173,6 +266,8 @@ def run_b200(args):
 		raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
 	torch.cuda.set_device(local_rank)
 	dev = torch.device('cuda', local_rank)
+	from photometry_b200 import affinity
+	aff = affinity.bind_to_gpu(local_rank) if not args.no_affinity else {"bound": False}
 	if rank == 0:
 		__graft_entry__.build()
 	if world > 1:
@@ -288,6 +383,31 @@ def run_b200(args):
 	e2e_value = world * ne * esteps / (ems * 1e-3)
 	# spot-check the transferred result against the resident one
 	assert torch.allclose(host_bkg[ne - 1], bkg[ne - 1].cpu(), rtol=1e-6, equal_nan=True)
+	# copy-only ceiling at this N: the same pinned buffers, the same bytes in both directions, no kernels
+	def copy_step():
+		s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+		ck = args.e2e_chunk
+		for a in range(0, ne, ck):
+			b = min(a + ck, ne)
+			with torch.cuda.stream(s_in):
+				cube[a:b].copy_(host_in[a:b], non_blocking=True)
+			with torch.cuda.stream(s_out):
+				host_bkg[a:b].copy_(bkg[a:b], non_blocking=True)
+				host_mask[a:b].copy_(mask[a:b], non_blocking=True)
+		torch.cuda.current_stream(dev).wait_stream(s_in); torch.cuda.current_stream(dev).wait_stream(s_out)
+	copy_step()
+	barrier()
+	f0.record()
+	for _ in range(esteps):
+		copy_step()
+	f1.record()
+	barrier()
+	cms = f0.elapsed_time(f1)
+	if world > 1:
+		t = torch.tensor([cms], dtype=torch.float64, device=dev)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		cms = float(t.item())
+	copy_ceiling = world * ne * esteps / (cms * 1e-3)
 	del host_in, host_bkg, host_mask
 
 	# ---- prepare path: fit + time smoothing + sumimage accumulation (+ NCCL reduce)
@@ -348,6 +468,29 @@ def run_b200(args):
 			"note": "bytes = cube elements read + written; reads are 60-byte row segments (32-byte sectors)"}
 		del res, flags_copy, cubes, srv
 
+	cpu_sample = cube[:min(max(os.cpu_count() or 1, 8), 64)].cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu) else None
+	# ---- north-star multi-GPU configurations (BASELINE.json configs[2], configs[3]), bounded; the resident benchmark cube
+	# is released first (a 4,000-FFI sector needs the memory)
+	config3 = config4 = parity = None
+	if args.configs:
+		del cube, bkg, mask
+		torch.cuda.empty_cache()
+		if world > 1:
+			parity = sharded_parity(pb.BackgroundFitter, dev, world, rank, dist)
+			# config 3: one 10-min-cadence sector of 4,000 FFIs, camera 4 ccd 1, time_smooth = 9 (w = 4), strong scaling
+			config3 = sector_path(pb, synth, dist, dev, rank, world, args.config3_ffis, 9, 4, 1, SEED + 100, chunk, args.streams, barrier,
+				"synthetic 10-min cadence sector, 2048x2048 x %d FFIs sharded by cadence over %d GPUs" % (args.config3_ffis, world))
+		# config 4: 200-s cadence camera, 4 CCDs one after the other, time_smooth = 27 (w = 13: the reference's 5,400-s window),
+		# per-CCD reduce; bounded to config4_ffis cadences per GPU and CCD
+		c4 = []
+		for ccd4 in (1, 2, 3, 4):
+			c4.append(sector_path(pb, synth, dist, dev, rank, world, args.config4_ffis * world, 27, 2, ccd4, SEED + 200 + 10 * ccd4, chunk, args.streams, barrier,
+				"synthetic 200-s cadence camera 2 ccd %d, %d cadences per GPU (bounded sample of 12,000 per CCD)" % (ccd4, args.config4_ffis)))
+		tot_ms = sum(x["ms"] for x in c4)
+		config4 = {"value": sum(x["total_ffis"] for x in c4) / (tot_ms * 1e-3), "unit": "FFIs/s", "scaling": "weak", "ccds": 4,
+			"ffis_per_gpu_per_ccd": args.config4_ffis, "time_smooth": 27, "halo_w": 13, "ms": tot_ms,
+			"halo_ms": sum(x["halo_ms"] for x in c4), "reduce_ms": sum(x["reduce_ms"] for x in c4), "per_ccd": c4}
+
 	if rank != 0:
 		if world > 1:
 			dist.destroy_process_group()
@@ -358,7 +501,7 @@ def run_b200(args):
 	if world == 1 and not args.no_cpu:
 		cores = os.cpu_count() or 1
 		ns = min(max(cores, 8), 64)
-		imgs = cube[:ns].cpu().numpy()
+		imgs = cpu_sample
 		try:
 			v, dt = cpu_reference_run(list(imgs), hdrs[:ns], cores)
 			cpu = {"value": v, "unit": "FFIs/s", "cores": cores, "kind": "port",
@@ -374,11 +517,16 @@ def run_b200(args):
 			"ffis_per_gpu": n, "ffis_per_launch": chunk, "streams": args.streams, "l2": "inputs (22.5 GB/GPU) larger than L2", "parallelism": f"cadence shards x{world}"},
 		"roofline": roofline, "cpu_baseline": cpu,
 		"e2e": {"value": e2e_value, "unit": "FFIs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-			"ffis_per_step": ne, "note": "one e2e step = fit_stack_host over a pinned host stack; results (bkg f32 + mask u8) copied back to pinned host memory"},
+			"ffis_per_step": ne, "copy_ceiling": copy_ceiling, "frac_of_ceiling": e2e_value / copy_ceiling,
+			"copy_ceiling_gbs": copy_ceiling * (4 + 5) * H * W / 1e9, "affinity": aff,
+			"note": "one e2e step = fit_stack_host over a pinned host stack; results (bkg f32 + mask u8) copied back to pinned host memory; "
+				"copy_ceiling = the same pinned buffers and bytes in both directions with no kernels, at this N"},
 		"gpu_launches": launches, "clocks": clocks,
 		"kernel_ms": {k: round(v, 3) for k, v in prof.items()}, "prepare_path": prep,
 		"shenanigans_path": shen, "stamps_path": stamps_path,
+		"config3_path": config3, "config4_path": config4, "sharded_parity": parity,
 	}
+	line.update(reference_probe())
 	print(json.dumps(line), flush=True)
 	if world > 1:
 		dist.destroy_process_group()
@@ -392,7 +540,11 @@ def main():
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--ffis', type=int, default=1340, help='FFIs per GPU per step')
 	ap.add_argument('--chunk', type=int, default=64, help='FFIs per tbk_fit_batch launch')
-	ap.add_argument('--streams', type=int, default=2, help='CUDA streams the chunks alternate between')
+	ap.add_argument('--streams', type=int, default=4, help='CUDA streams the chunks alternate between')
+	ap.add_argument('--no-configs', dest='configs', action='store_false', help='skip the config 3 / config 4 / sharded parity legs')
+	ap.add_argument('--config3-ffis', type=int, default=4000, help='cadences of the sharded 10-min sector (config 3, N > 1 only)')
+	ap.add_argument('--config4-ffis', type=int, default=192, help='cadences per GPU and CCD of the bounded 200-s camera (config 4)')
+	ap.add_argument('--no-affinity', action='store_true', help='do not bind the process to the CPUs local to its GPU')
 	ap.add_argument('--e2e-ffis', type=int, default=512, help='pinned host stack size for the end-to-end leg')
 	ap.add_argument('--e2e-chunk', type=int, default=16)
 	ap.add_argument('--prepare-ffis', type=int, default=256)

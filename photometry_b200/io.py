@@ -44,6 +44,21 @@ def _parse_card(card):
 		return key, val
 
 
+def backfill_ffiindex(hdr):
+	"""
+	io.py:56-67: files from before sector 6 carry no FFIINDEX; the cadence number is extrapolated linearly from the
+	mid-exposure time (30-min cadence files only).  Modifies and returns ``hdr``.
+	"""
+	if 'FFIINDEX' not in hdr and hdr['EXPOSURE'] * 86400 > 1000:
+		time = 0.5 * (hdr['TSTART'] + hdr['TSTOP'])
+		timecorr = hdr.get('BARYCORR', 0)
+		first_time = 0.5 * (1325.317007851970 + 1325.337841177751) - 3.9072474e-03
+		timedelt = 1800 / 86400
+		offset = 4697 - first_time / timedelt
+		hdr['FFIINDEX'] = np.round((time - timecorr) / timedelt + offset)
+	return hdr
+
+
 def scan_fits(buf):
 	"""Yield (header dict, data offset, shape, bitpix) for every HDU of an in-memory FITS file."""
 	pos = 0
@@ -72,11 +87,12 @@ def scan_fits(buf):
 		pos += (nbytes + _BLOCK - 1) // _BLOCK * _BLOCK
 
 
-def read_ffi_raw(path):
+def read_ffi_raw(path, with_err=False):
 	"""
 	Read a TESS FFI FITS(.gz) file WITHOUT decoding the pixels: returns
 	``(merged header, raw big-endian bytes of the image HDU, naxis1, naxis2)`` for the device-side decode
-	(:func:`photometry_b200.ingest.load_ffi_stack`).  Raises ValueError for non-TESS files (io.py:46).
+	(:func:`photometry_b200.ingest.load_ffi_stack`); with ``with_err`` a fifth item, the raw bytes of the uncertainty
+	HDU (``hdu[2]``, io.py:48).  Raises ValueError for non-TESS files (io.py:46).
 	"""
 	opener = gzip.open if str(path).endswith('.gz') else open
 	with opener(path, 'rb') as fid:
@@ -84,21 +100,20 @@ def read_ffi_raw(path):
 	hdus = []
 	for item in scan_fits(buf):
 		hdus.append(item)
-		if len(hdus) == 2:
+		if len(hdus) == (3 if with_err else 2):
 			break
 	if len(hdus) < 2:
 		raise ValueError(f"{path}: no image extension")
 	hdr0, (hdr1, off, shape, bitpix) = hdus[0][0], hdus[1]
 	if hdr0.get('TELESCOP') != 'TESS' or hdr1.get('NAXIS1') != 2136 or hdr1.get('NAXIS2') != 2078 or bitpix != -32:
 		raise ValueError(f"{path}: not a TESS full-frame image")
-	hdr = dict(hdr0)
-	hdr.update(hdr1)
-	if 'FFIINDEX' not in hdr and hdr['EXPOSURE'] * 86400 > 1000:
-		time = 0.5 * (hdr['TSTART'] + hdr['TSTOP'])
-		first_time = 0.5 * (1325.317007851970 + 1325.337841177751) - 3.9072474e-03
-		timedelt = 1800 / 86400
-		hdr['FFIINDEX'] = np.round((time - hdr.get('BARYCORR', 0)) / timedelt + (4697 - first_time / timedelt))
+	hdr = backfill_ffiindex({**hdr0, **hdr1})
 	n1, n2 = shape[1], shape[0]
+	if with_err:
+		if len(hdus) < 3 or hdus[2][2] != shape or hdus[2][3] != -32:
+			raise ValueError(f"{path}: no uncertainty extension of the image's shape")
+		off2 = hdus[2][1]
+		return hdr, memoryview(buf)[off:off + 4 * n1 * n2], n1, n2, memoryview(buf)[off2:off2 + 4 * n1 * n2]
 	return hdr, memoryview(buf)[off:off + 4 * n1 * n2], n1, n2
 
 
@@ -108,35 +123,13 @@ def read_fits_hdus(path):
 	with opener(path, 'rb') as fid:
 		buf = fid.read()
 	hdus = []
-	pos = 0
-	while pos + _BLOCK <= len(buf):
-		hdr = {}
-		done = False
-		while not done:
-			block = buf[pos:pos + _BLOCK].decode('ascii', 'replace')
-			pos += _BLOCK
-			for i in range(0, _BLOCK, 80):
-				card = block[i:i + 80]
-				if card.startswith('END') and card[3:].strip() == '':
-					done = True
-					break
-				key, val = _parse_card(card)
-				if val is not None and key not in hdr:
-					hdr[key] = val
-			if pos >= len(buf) and not done:
-				raise ValueError("truncated FITS header")
-		naxis = int(hdr.get('NAXIS', 0))
-		shape = [int(hdr[f'NAXIS{i}']) for i in range(naxis, 0, -1)]
-		bitpix = int(hdr.get('BITPIX', 8))
-		nbytes = abs(bitpix) // 8 * int(np.prod(shape)) if naxis else 0
-		nbytes = (nbytes + int(hdr.get('PCOUNT', 0))) * int(hdr.get('GCOUNT', 1)) if naxis else 0
+	for hdr, pos, shape, bitpix in scan_fits(buf):
 		data = None
-		if naxis and hdr.get('XTENSION', 'IMAGE').strip() == 'IMAGE':
+		if shape and hdr.get('XTENSION', 'IMAGE').strip() == 'IMAGE':
 			dt = {8: 'u1', 16: '>i2', 32: '>i4', 64: '>i8', -32: '>f4', -64: '>f8'}[bitpix]
 			data = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape)), offset=pos).reshape(shape)
 			if 'BSCALE' in hdr or 'BZERO' in hdr:
 				data = data * hdr.get('BSCALE', 1) + hdr.get('BZERO', 0)
-		pos += (nbytes + _BLOCK - 1) // _BLOCK * _BLOCK
 		hdus.append((hdr, data))
 	return hdus
 
@@ -169,16 +162,7 @@ class FFIImage:
 					data = np.asarray(hdus[1][1][0:2048, 44:2092], dtype='float32')
 					self.uncertainty = np.asarray(hdus[2][1][0:2048, 44:2092], dtype='float32')
 					self.is_tess = True
-					hdr = dict(hdr0)
-					hdr.update(hdus[1][0])
-					if 'FFIINDEX' not in hdr and hdr['EXPOSURE'] * 86400 > 1000:
-						# io.py:56-67: linear cadence number extrapolation before sector 6
-						time = 0.5 * (hdr['TSTART'] + hdr['TSTOP'])
-						timecorr = hdr.get('BARYCORR', 0)
-						first_time = 0.5 * (1325.317007851970 + 1325.337841177751) - 3.9072474e-03
-						timedelt = 1800 / 86400
-						offset = 4697 - first_time / timedelt
-						hdr['FFIINDEX'] = np.round((time - timecorr) / timedelt + offset)
+					hdr = backfill_ffiindex({**hdr0, **hdus[1][0]})
 				else:
 					data = np.asarray(hdus[0][1], dtype='float32')
 					if len(hdus) > 1 and hdus[1][1] is not None:

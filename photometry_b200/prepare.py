@@ -48,16 +48,28 @@ def exchange_halos(frames, w, group=None):
 
 
 def reduce_accumulators(sum_, nimg, used, n_local, group=None):
-	"""Sum-reduce SumImage / Nimg / UsedInBackgrounds to rank 0 and return the global file count."""
+	"""
+	Sum-reduce SumImage / Nimg / UsedInBackgrounds to rank 0 and return the global file count: ONE reduce of one packed
+	float64 buffer [SumImage | Nimg | Used | count] -- the counters are integers far below 2**53, so their float64 sums are
+	exact -- followed by one small broadcast of the count (every rank needs ``numfiles``).
+	"""
 	if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
 		return n_local
 	dst = dist.get_global_rank(group, 0) if group is not None else 0
-	dist.reduce(sum_, dst=dst, op=dist.ReduceOp.SUM, group=group)
-	dist.reduce(nimg, dst=dst, op=dist.ReduceOp.SUM, group=group)
-	dist.reduce(used, dst=dst, op=dist.ReduceOp.SUM, group=group)
-	cnt = torch.tensor([n_local], dtype=torch.int64, device=sum_.device)
-	dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-	return int(cnt.item())
+	npix = sum_.numel()
+	pack = torch.empty(3 * npix + 1, dtype=torch.float64, device=sum_.device)
+	pack[:npix] = sum_.reshape(-1)
+	pack[npix:2 * npix] = nimg.reshape(-1)
+	pack[2 * npix:3 * npix] = used.reshape(-1)
+	pack[3 * npix] = float(n_local)
+	dist.reduce(pack, dst=dst, op=dist.ReduceOp.SUM, group=group)
+	cnt = pack[3 * npix:].clone()
+	dist.broadcast(cnt, src=dst, group=group)
+	if dist.get_rank(group) == 0:
+		sum_.copy_(pack[:npix].view_as(sum_))
+		nimg.copy_(pack[npix:2 * npix].view_as(nimg))       # float64 -> int32, exact
+		used.copy_(pack[2 * npix:3 * npix].view_as(used))
+	return int(round(float(cnt.item())))
 
 
 @dataclass
@@ -90,7 +102,7 @@ def check_status(status, first_cadence=0):
 
 
 def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, keep_images=True,
-	backgrounds_pixels_threshold=0.5, group=None):
+	backgrounds_pixels_threshold=0.5, group=None, timings=None, nstreams=1):
 	"""
 	Run prepare.py:265-470 for this rank's shard.
 
@@ -98,7 +110,8 @@ def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, k
 	cube        float32 CUDA tensor [n_local, H, W], time ordered
 	meta        ``tbk_ffi_meta`` numpy array [n_local]
 	time_smooth smoothing window in cadences (prepare.py:258: 3 at 1800 s, 9 at 600 s)
-	chunk       FFIs per ``tbk_fit_batch`` launch
+	chunk       FFIs per ``tbk_fit_batch`` launch;  nstreams > 1 runs the chunks on alternating CUDA streams
+	timings     optional dict: receives the device time (ms) of the halo exchange and of the reduce ('halo_ms', 'reduce_ms')
 	"""
 	from ._lib import STATUS_DTYPE
 	n = cube.shape[0]
@@ -110,12 +123,18 @@ def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, k
 	flags = torch.empty(cube.shape, dtype=torch.uint8, device=dev)
 	status = torch.empty(n * STATUS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
 	ssz = STATUS_DTYPE.itemsize
-	for i in range(0, n, chunk):
-		j = min(i + chunk, n)
-		fitter.fit(cube[i:j], meta_d[i * isz:j * isz], None if extra_mask is None else extra_mask[i:j],
-			bkg_out=bkg_us[i:j], mask_out=flags[i:j], status_out=status[i * ssz:j * ssz])
+	if nstreams > 1:
+		fitter.fit_stack(cube, meta_d, bkg_us, flags, chunk=chunk, extra_mask=extra_mask, status_out=status, nstreams=nstreams)
+	else:
+		for i in range(0, n, chunk):
+			j = min(i + chunk, n)
+			fitter.fit(cube[i:j], meta_d[i * isz:j * isz], None if extra_mask is None else extra_mask[i:j],
+				bkg_out=bkg_us[i:j], mask_out=flags[i:j], status_out=status[i * ssz:j * ssz])
 	w = int(time_smooth) // 2
+	ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
+	if ev: ev[0].record()
 	halo_lo, halo_hi = exchange_halos(bkg_us, w, group)
+	if ev: ev[1].record()
 	bkg = fitter.time_smooth(bkg_us, w, halo_lo, halo_hi)
 	H, W = cube.shape[1:]
 	sum_ = torch.zeros((H, W), dtype=torch.float64, device=dev)
@@ -123,7 +142,13 @@ def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, k
 	used = torch.zeros((H, W), dtype=torch.int32, device=dev)
 	images = torch.empty_like(cube) if keep_images else None
 	fitter.sum_accumulate(cube, bkg, flags, meta_d, sum_, nimg, used, flux_out=images)
+	if ev: ev[2].record()
 	numfiles = reduce_accumulators(sum_, nimg, used, n, group)
+	if ev:
+		ev[3].record()
+		torch.cuda.synchronize(dev)
+		timings['halo_ms'] = ev[0].elapsed_time(ev[1])
+		timings['reduce_ms'] = ev[2].elapsed_time(ev[3])
 	is_root = not (dist.is_available() and dist.is_initialized()) or dist.get_rank(group) == 0
 	sumimage = pixels_used = None
 	if is_root:
