@@ -418,8 +418,9 @@ def run_b200(args):
 		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 		pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True)
 		barrier()
+		ptm = {}
 		g0.record()
-		res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True)
+		res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, timings=ptm)
 		g1.record()
 		barrier()
 		pms = g0.elapsed_time(g1)
@@ -428,7 +429,7 @@ def run_b200(args):
 			dist.all_reduce(t, op=dist.ReduceOp.MAX)
 			pms = float(t.item())
 		prep = {"value": world * np_ / (pms * 1e-3), "unit": "FFIs/s", "ffis_per_gpu": np_, "numfiles": res.numfiles,
-			"stages": "fit + time_smooth(w=1) + sum_accumulate + reduce + finalize"}
+			"stages": "fit + time_smooth(w=1) + sum_accumulate + reduce + finalize", "ms": pms, "halo_ms": ptm.get('halo_ms'), "reduce_ms": ptm.get('reduce_ms')}
 		# ---- background shenanigans (prepare.py:514-622) on the same frames: 15 x 15 median indicator per cadence,
 		# robust mean over shuffled blocks (cadence -> row-slab exchange when N > 1), flagging
 		flags_copy = res.pixel_flags.clone()

@@ -507,3 +507,47 @@ def test_device_log10():
 	p10 = 10.0 ** np.arange(0, 16)
 	sel = np.isin(x, p10)
 	assert np.abs(got[sel] - np.round(ref[sel])).max() <= 4.5e-16 * 15
+
+
+# ---- the prepare driver on the GPU engine -----------------------------------------------------------
+def test_driver_gpu_products_equal_prepare_stack(tmp_path):
+	"""
+	prepare_photometry (FITS files -> resumable product store, GpuEngine) writes exactly what prepare_stack computes for
+	the same stack held on the device: smoothed backgrounds, flags, images, image errors, sum image, used-pixel map.
+	"""
+	import gzip
+	from test_host_logic import _hdu
+	from photometry_b200 import prepare_driver, synth
+	from photometry_b200.store import open_store
+	n = 5
+	stack = synth.synth_stack_numpy(n, 2048, 2048, camera=1, ccd=4, seed=3, n_stars=4000)
+	paths = []
+	for k in range(n):
+		raw = np.full((2078, 2136), 50.0, dtype='float32')
+		raw[0:2048, 44:2092] = stack[k]
+		err = np.full((2078, 2136), 2.0 + k, dtype='float32')
+		prim = _hdu([('SIMPLE', True), ('BITPIX', 8), ('NAXIS', 0), ('EXTEND', True), ('TELESCOP', 'TESS'), ('CAMERA', 1), ('CCD', 4), ('DATA_REL', 1)])
+		ext = [('XTENSION', 'IMAGE'), ('BITPIX', -32), ('NAXIS', 2), ('NAXIS1', 2136), ('NAXIS2', 2078), ('PCOUNT', 0), ('GCOUNT', 1),
+			('TSTART', 1330.0 + 0.02 * k), ('TSTOP', 1330.02 + 0.02 * k), ('FFIINDEX', 4700 + k), ('DQUALITY', 32 if k == 2 else 0), ('BARYCORR', 0.002)]
+		path = str(tmp_path / f'tess2018{k:09d}-s0001-1-4-0120-s_ffic.fits.gz')
+		with gzip.open(path, 'wb', compresslevel=1) as fid:
+			fid.write(prim + _hdu(ext, raw) + _hdu(ext[:7], err))
+		paths.append(path)
+	out = prepare_driver.prepare_photometry(str(tmp_path), sectors=1, cameras=1, ccds=4, store_backend='npy', batch=2)
+	assert len(out) == 1
+	# the same stack through the device-resident path (camera 1 / ccd 4 before cadence 4724: Mars columns -> ManualExclude + IDW fill)
+	hdrs = [dict(CAMERA=1, CCD=4, TSTART=1330.0 + 0.02 * k, TSTOP=1330.02 + 0.02 * k, FFIINDEX=4700 + k, DQUALITY=32 if k == 2 else 0) for k in range(n)]
+	fit = pb.BackgroundFitter((2048, 2048), True, 1, 4)
+	res = pb.prepare_stack(fit, torch.from_numpy(stack).cuda(), pb.meta_from_headers(hdrs), time_smooth=3, chunk=2)
+	with open_store(out[0], 'a', 'npy') as hdf:
+		for k in range(n):
+			name = f'{k:04d}'
+			assert np.array_equal(np.asarray(hdf['backgrounds'][name]), res.backgrounds[k].cpu().numpy(), equal_nan=True)
+			assert np.array_equal(np.asarray(hdf['pixel_flags'][name]), res.pixel_flags[k].cpu().numpy())
+			assert np.array_equal(np.asarray(hdf['images'][name]), res.images[k].cpu().numpy(), equal_nan=True)
+			e = np.asarray(hdf['images_err'][name])
+			assert np.isnan(e[:, 1536:]).all() and (e[:, :1536] == 2.0 + k).all()          # ManualExclude -> NaN (prepare.py:423-425)
+		assert np.allclose(np.asarray(hdf['sumimage']), res.sumimage.cpu().numpy(), rtol=1e-12, equal_nan=True)
+		assert np.array_equal(np.asarray(hdf['backgrounds_pixels_used']).astype(np.uint8), res.backgrounds_pixels_used.cpu().numpy())
+		assert list(np.asarray(hdf['cadenceno'])) == [4700 + k for k in range(n)] and int(np.asarray(hdf['quality'])[2]) == 32
+		assert hdf.require_group('images').attrs['CAMERA'] == 1 and hdf.require_group('images').attrs['CADENCE'] == 1800
