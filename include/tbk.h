@@ -190,6 +190,23 @@ int tbk_bkgshe_flag(const float* ind, const double* mean, int B, size_t npix, do
 int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, const int32_t* stamps,
 	const int64_t* out_offsets, int S, void* out, void* stream);
 
+/*
+ * Image movement kernels (photometry/image_motion.py:74-111 ``_prepare_flux``, :182-258 ``calc_kernel`` with
+ * warpmode='translation'; driver photometry/prepare.py:678-698).  All pointers are device pointers; no plan is needed.
+ *
+ * tbk_motion_prepare: prepared[k] = float32(scharr(-1 + 2 (L - min L) / |max L - min L|)) with L = log10(images[k] -
+ *   nanmin(images[k]) + 1), NaN -> 0 (skimage 0.19 ``scharr``: 3 x 3, mode='reflect').  scratch: 16 bytes per frame.
+ * tbk_motion_ecc: ``cv2.findTransformECC(ref_prepared, prepared[k], eye(2, 3), MOTION_TRANSLATION, (COUNT | EPS, max_iter,
+ *   eps), mask of ones, gaussFiltSize = 5)`` for every frame of the batch: out[k] = {dx, dy, rho, iterations}; dx = dy = NaN
+ *   where OpenCV raises (the reference logs and stores NaN, image_motion.py:239-241).  The call synchronises the stream
+ *   every few iterations to learn whether every frame has met its criterion.
+ *   workspace: tbk_motion_workspace_bytes(B, H, W) bytes.
+ */
+int tbk_motion_prepare(const float* images, int B, int H, int W, float* prepared, void* scratch, void* stream);
+size_t tbk_motion_workspace_bytes(int B, int H, int W);
+int tbk_motion_ecc(const float* ref_prepared, const float* prepared, int B, int H, int W, int max_iter, double eps,
+	void* workspace, double* out, void* stream);
+
 /* Diagnostics: out[i] = the device log10 used for the ring samples (table-driven, see tbk_common.cuh) of in[i];
  * both device pointers.  Lets the tests bound its error against a host log10. */
 int tbk_debug_log10(const double* in, double* out, int n, void* stream);

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIBPATH = os.path.join(LIBDIR, 'libtbk.so')
-SOURCES = ['tbk_api.cu', 'tbk_fit.cu', 'tbk_prepare.cu', 'tbk_shenanigans.cu']
+SOURCES = ['tbk_api.cu', 'tbk_fit.cu', 'tbk_prepare.cu', 'tbk_shenanigans.cu', 'tbk_motion.cu']
 NVCC_FLAGS = [
 	'-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
 	'-Xcompiler', '-fPIC', '-diag-suppress', '177',

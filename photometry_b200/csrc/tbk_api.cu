@@ -445,6 +445,27 @@ extern "C" int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H
 	return tbk_launch_gather_stamps(stack, elem_bytes, N, H, W, (const int*)stamps, (const long long*)out_offsets, S, tiles_x, out, (cudaStream_t)stream);
 }
 
+extern "C" int tbk_motion_prepare(const float* images, int B, int H, int W, float* prepared, void* scratch, void* stream)
+{
+	if (!images || !prepared || !scratch || B <= 0 || H < 3 || W < 3 || B > 65535) { tbk_set_error("tbk_motion_prepare: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_motion_prepare(images, B, H, W, prepared, (unsigned*)scratch, (cudaStream_t)stream);
+}
+
+extern "C" size_t tbk_motion_workspace_bytes(int B, int H, int W)
+{
+	if (B <= 0 || H <= 0 || W <= 0) return 0;
+	return tbk_motion_workspace(B, H, W);
+}
+
+extern "C" int tbk_motion_ecc(const float* ref_prepared, const float* prepared, int B, int H, int W, int max_iter, double eps,
+	void* workspace, double* out, void* stream)
+{
+	if (!ref_prepared || !prepared || !workspace || !out || B <= 0 || B > 65535 || H < 5 || W < 5 || max_iter < 1 || ((uintptr_t)workspace & 255)) {
+		tbk_set_error("tbk_motion_ecc: bad argument"); return TBK_ERR_INVALID;
+	}
+	return tbk_launch_motion_ecc(ref_prepared, prepared, B, H, W, max_iter, eps, workspace, out, (cudaStream_t)stream);
+}
+
 extern "C" int tbk_debug_log10(const double* in, double* out, int n, void* stream)
 {
 	if (!in || !out || n <= 0) { tbk_set_error("tbk_debug_log10: bad argument"); return TBK_ERR_INVALID; }

@@ -37,3 +37,9 @@ int tbk_launch_gather_stamps(const void* stack, int elem_bytes, int N, int H, in
 	const long long* offs, int S, int tiles_x, void* out, cudaStream_t st);
 int tbk_launch_log10(const double* in, double* out, int n, cudaStream_t st);
 int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row0, int col0, int H, int W, float* out, cudaStream_t st);
+
+// tbk_motion.cu
+int tbk_launch_motion_prepare(const float* flux, int B, int H, int W, float* out, unsigned* scratch, cudaStream_t st);
+size_t tbk_motion_workspace(int B, int H, int W);
+int tbk_launch_motion_ecc(const float* ref_prepared, const float* prepared, int B, int H, int W, int max_iter, double eps,
+	void* workspace, double* out, cudaStream_t st);
