@@ -191,6 +191,14 @@ int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H, int W, co
 	const int64_t* out_offsets, int S, void* out, void* stream);
 
 /*
+ * Catalog-driven star mask -- an EXTENSION: the reference accepts a ``catalog`` argument but does not use it yet
+ * (photometry/backgrounds.py:64-65, TODO at :90).  stars: double [S][3] = (column, row, radius in pixels) in science-pixel
+ * coordinates (device); every pixel with (x - column)^2 + (y - row)^2 <= radius^2 is set to 1 in ``mask`` (uint8 [H, W],
+ * device, OR-ed into -- the caller zeroes it first).  The result is what tbk_fit_batch takes as ``extra_mask``.
+ */
+int tbk_star_mask(const double* stars, int S, int H, int W, uint8_t* mask, void* stream);
+
+/*
  * Image movement kernels (photometry/image_motion.py:74-111 ``_prepare_flux``, :182-258 ``calc_kernel`` with
  * warpmode='translation'; driver photometry/prepare.py:678-698).  All pointers are device pointers; no plan is needed.
  *

@@ -16,7 +16,7 @@ checked in ``tests/test_oracle_kat.py``.
 from .backgrounds_oracle import (  # noqa: F401
 	FFIImageLite, fit_background, pixel_manual_exclude, move_median_central,
 	reduce_mode, kde_density, sigma_clip_bounds, sextractor_background, Background2DOracle,
-	radial_geometry, XYCEN,
+	radial_geometry, XYCEN, star_mask, star_radius,
 )
 from .prepare_oracle import (  # noqa: F401
 	time_smooth_backgrounds, sumimage_accumulate, prepare_stack,

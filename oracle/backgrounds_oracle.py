@@ -83,6 +83,30 @@ def pixel_manual_exclude(img):
 
 
 # --------------------------------------------------------------------------------------------------
+def star_radius(tmag):
+	"""Extension (photometry_b200/starmask.py): r = clip(4 * 10**(-0.1 (Tmag - 10)), 1.5, 40) pixels."""
+	return np.clip(4.0 * 10.0 ** (-0.1 * (np.asarray(tmag, dtype='float64') - 10.0)), 1.5, 40.0)
+
+
+def star_mask(shape, catalog):
+	"""
+	Extension beyond the reference (its ``catalog`` argument is unused, backgrounds.py:64-65, 90): boolean [H, W], True where
+	(x - column)**2 + (y - row)**2 <= r(Tmag)**2 for a catalog row (column, row, Tmag) in science-pixel coordinates.
+	"""
+	H, W = shape
+	mask = np.zeros((H, W), dtype=bool)
+	cat = np.asarray(catalog, dtype='float64').reshape(-1, 3)
+	for (sx, sy, tm), r in zip(cat, star_radius(cat[:, 2]) if cat.size else []):
+		x0, x1 = max(0, int(np.ceil(sx - r))), min(W - 1, int(np.floor(sx + r)))
+		y0, y1 = max(0, int(np.ceil(sy - r))), min(H - 1, int(np.floor(sy + r)))
+		if x1 < x0 or y1 < y0:
+			continue
+		yy, xx = np.mgrid[y0:y1 + 1, x0:x1 + 1].astype('float64')
+		mask[y0:y1 + 1, x0:x1 + 1] |= ((xx - sx) * (xx - sx) + (yy - sy) * (yy - sy)) <= r * r
+	return mask
+
+
+# --------------------------------------------------------------------------------------------------
 def _nanmedian1d(x):
 	x = np.asarray(x, dtype='float64')
 	x = x[~np.isnan(x)]

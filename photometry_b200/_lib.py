@@ -58,6 +58,7 @@ SIGNATURES = {
 	'tbk_launch_count': (C.c_ulonglong, []),
 	'tbk_workspace_layout': (C.c_int, [_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 	'tbk_debug_idw_neighbors': (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
+	'tbk_star_mask': (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
 	'tbk_motion_prepare': (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
 	'tbk_motion_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
 	'tbk_motion_ecc': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _p, _p, _p]),

@@ -239,7 +239,9 @@ def fit_background(image, catalog=None, flux_cutoff=8e4, bkgiters=3, radial_cuto
 
 	Parameters:
 		image (ndarray, str or :class:`FFIImage`): 2D image or path to a FITS(.gz)/NPY file.
-		catalog: unused (as in the reference, backgrounds.py:64-65).
+		catalog: ``None`` (default) reproduces the reference, where the argument is accepted but unused (backgrounds.py:64-65).
+			Extension: an array [S, 3] of (column, row, Tmag) in science-pixel coordinates masks a disc around every star
+			(:mod:`photometry_b200.starmask`; OR-ed into the mask at the point of backgrounds.py:90).
 		flux_cutoff, bkgiters, radial_cutoff, radial_pixel_step, radial_smooth: see the reference.
 
 	Returns:
@@ -261,12 +263,23 @@ def fit_background(image, catalog=None, flux_cutoff=8e4, bkgiters=3, radial_cuto
 	fitter = _cached_fitter(data.shape, img0.is_tess, int(camera or 0), int(ccd or 0), float(flux_cutoff), int(bkgiters),
 		float(radial_cutoff), float(radial_pixel_step), int(radial_smooth or 0), torch.cuda.current_device())
 	meta = meta_from_headers([hdr]) if img0.is_tess else make_meta(1)
-	pinned = torch.from_numpy(data).pin_memory()
-	cube = pinned.to(fitter.device, non_blocking=True).unsqueeze(0)
-	bkg, mask, status = fitter.fit(cube, meta)
-	bkg_h = bkg[0].to('cpu', non_blocking=False).numpy().astype('float64')
-	mask_h = mask[0].cpu().numpy().astype(bool)
-	st = fitter.status_to_numpy(status)[0]
+	# one set of pinned staging buffers per cached fitter, reused across calls (the reference calls this once per FFI)
+	stg = getattr(fitter, '_staging', None)
+	if stg is None:
+		stg = fitter._staging = (torch.empty(data.shape, dtype=torch.float32).pin_memory(), torch.empty(data.shape, dtype=torch.float32).pin_memory(),
+			torch.empty(data.shape, dtype=torch.uint8).pin_memory())
+	stg[0].copy_(torch.from_numpy(data))
+	cube = stg[0].to(fitter.device, non_blocking=True).unsqueeze(0)
+	extra = None
+	if catalog is not None:
+		from .starmask import star_mask
+		extra = star_mask(data.shape, catalog, device=fitter.device.index).unsqueeze(0)
+	bkg, mask, status = fitter.fit(cube, meta, extra_mask=extra)
+	stg[1].copy_(bkg[0], non_blocking=True)
+	stg[2].copy_(mask[0], non_blocking=True)
+	st = fitter.status_to_numpy(status)[0]       # synchronises
+	bkg_h = stg[1].numpy().astype('float64')
+	mask_h = stg[2].numpy().astype(bool)
 	if st['no_good_mesh']:
 		# photutils: "All meshes contain > 2048 masked pixels" (uncaught in the reference)
 		raise ValueError("All meshes contain > 2048 (50.0 percent per mesh) masked pixels. Please check your data or increase \"exclude_percentile\".")

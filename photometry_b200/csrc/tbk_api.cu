@@ -289,6 +289,16 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 		const double ang = -2.0 * M_PI * (double)k / (double)TBK_KDE_M;
 		tw[k] = make_double2(std::cos(ang), std::sin(ang));
 	}
+	{
+		// IDW pattern cache: zeroed device words, written only by k_mesh_finalize
+		const size_t nwords = (P.ntiles + 31) / 32;
+		const size_t words = 1 + TBK_IDW_CACHE * (1 + nwords + ((size_t)P.ntiles * 10 + 1) / 2);
+		void* d = nullptr;
+		CUDA_TRY(cudaMalloc(&d, words * sizeof(uint32_t)));
+		p->allocs.push_back(d);
+		CUDA_TRY(cudaMemset(d, 0, words * sizeof(uint32_t)));
+		P.idw_cache = (uint32_t*)d;
+	}
 	int rc;
 	if ((rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
 		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
@@ -443,6 +453,12 @@ extern "C" int tbk_gather_stamps(const void* stack, int elem_bytes, int N, int H
 	// enough CTAs per stamp to fill the device for a handful of stamps, few enough that thousands of stamps stay cheap
 	const int tiles_x = S >= 1184 ? 1 : (1184 + S - 1) / S;
 	return tbk_launch_gather_stamps(stack, elem_bytes, N, H, W, (const int*)stamps, (const long long*)out_offsets, S, tiles_x, out, (cudaStream_t)stream);
+}
+
+extern "C" int tbk_star_mask(const double* stars, int S, int H, int W, uint8_t* mask, void* stream)
+{
+	if (!stars || !mask || S <= 0 || H <= 0 || W <= 0) { tbk_set_error("tbk_star_mask: bad argument"); return TBK_ERR_INVALID; }
+	return tbk_launch_star_mask(stars, S, H, W, mask, (cudaStream_t)stream);
 }
 
 extern "C" int tbk_motion_prepare(const float* images, int B, int H, int W, float* prepared, void* scratch, void* stream)

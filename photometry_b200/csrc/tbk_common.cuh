@@ -11,6 +11,7 @@
 #define TBK_CAND 256          // max candidates resolved by rank counting
 #define TBK_KDE_M 2048        // KDE grid (2**ceil(log2(2000)), statsmodels kdensityfft)
 #define TBK_NPIX_TILE (TBK_TILE * TBK_TILE)
+#define TBK_IDW_CACHE 16      // good-mesh patterns whose IDW neighbour tables a plan remembers
 
 // ---------------------------------------------------------------------------------------------
 // Static per-plan description, passed by value to kernels.
@@ -35,6 +36,7 @@ struct PlanDev {
 	const int* ringtile_id;     // [n_ringtiles] mesh id
 	const int* ringtile_ptr;    // [n_ringtiles + 1] CSR offsets into ringtile_ent
 	const unsigned* ringtile_ent; // [nringpix] (index into the ring-ordered sample array << 12) | (row << 6 | col) within the mesh
+	uint32_t* idw_cache;        // [1 + TBK_IDW_CACHE entries]: entries used, then {state, good-mesh bitmap, neighbour table} each
 	const double* zoom_w;       // [64][4] cubic B-spline weights per sub-tile phase
 	const double2* twiddle;     // [TBK_KDE_M/2] exp(-2 pi i k / M)
 };

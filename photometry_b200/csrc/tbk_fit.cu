@@ -1929,7 +1929,33 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 			if (bits[1 + w] != m) { s_same = 0; bits[1 + w] = m; }
 		}
 		__syncthreads();
-		const bool reuse = s_same != 0;
+		bool reuse = s_same != 0;
+		// Not this FFI's previous pattern: look the bitmap up in the plan's pattern cache (P.idw_cache: a few entries of
+		// {state, bitmap, neighbour table} shared by every FFI, batch and stream of the plan).  Whole stacks repeat one pattern
+		// (the Mars frames of sector 1 exclude the same eight mesh columns in every cadence), so the tree is built once.
+		const size_t cstride = 1 + (size_t)nwords + ((size_t)nt_tiles * KDT_K + 1) / 2;    // words per cache entry
+		__shared__ int s_hit;
+		if (!reuse) {
+			if (tid == 0) s_hit = -1;
+			__syncthreads();
+			for (int e = 0; e < TBK_IDW_CACHE; ++e) {
+				const uint32_t* ce = P.idw_cache + 1 + e * cstride;
+				if (*(volatile const uint32_t*)ce != 2u) continue;     // uniform: every thread reads the same word
+				__threadfence();
+				int same = 1;
+				for (int w = tid; w < nwords; w += nt) same &= (ce[1 + w] == bits[1 + w]);
+				if (__syncthreads_and(same)) { if (tid == 0) s_hit = e; break; }
+			}
+			__syncthreads();
+			if (s_hit >= 0) {
+				const uint16_t* ctab = reinterpret_cast<const uint16_t*>(P.idw_cache + 1 + s_hit * cstride + 1 + nwords);
+				for (int i = tid; i < nt_tiles * KDT_K; i += nt) tab[i] = ctab[i];
+				if (tid == 0) bits[0] = 1u;
+				__syncthreads();
+				reuse = true;
+			}
+		}
+		const bool built = !reuse;
 		if (!reuse) {
 			// good meshes in increasing mesh id (the reference's point order), packed with their coordinates
 			int base = 0;
@@ -1975,6 +2001,24 @@ __global__ void __launch_bounds__(1024) k_mesh_finalize(PlanDev P, Workspace ws,
 		}
 		__syncthreads();
 		if (s_ovf && tid == 0 && status) status[b].n_excluded[round] = -1;   // cannot happen for <= 4096 meshes (checked by the tests)
+		// publish a freshly built table (entries for good meshes are never read: fill them so the copy is complete)
+		if (built && !s_ovf) {
+			__shared__ int s_slot;
+			if (tid == 0) { const uint32_t k = atomicAdd(P.idw_cache, 1u); s_slot = k < TBK_IDW_CACHE ? (int)k : -1; }
+			__syncthreads();
+			if (s_slot >= 0) {
+				uint32_t* ce = P.idw_cache + 1 + s_slot * cstride;
+				for (int w = tid; w < nwords; w += nt) ce[1 + w] = bits[1 + w];
+				uint16_t* ctab = reinterpret_cast<uint16_t*>(ce + 1 + nwords);
+				for (int t = tid; t < nt_tiles; t += nt) {
+					const bool excluded = !(val[t] == val[t]);
+					for (int j = 0; j < KDT_K; ++j) ctab[(size_t)t * KDT_K + j] = excluded ? tab[(size_t)t * KDT_K + j] : (uint16_t)0xFFFF;
+				}
+				__threadfence();
+				__syncthreads();
+				if (tid == 0) *(volatile uint32_t*)ce = 2u;
+			}
+		}
 	} else {
 		for (int t = tid; t < nt_tiles; t += nt) fil[t] = val[t];
 	}

@@ -43,3 +43,4 @@ int tbk_launch_motion_prepare(const float* flux, int B, int H, int W, float* out
 size_t tbk_motion_workspace(int B, int H, int W);
 int tbk_launch_motion_ecc(const float* ref_prepared, const float* prepared, int B, int H, int W, int max_iter, double eps,
 	void* workspace, double* out, cudaStream_t st);
+int tbk_launch_star_mask(const double* stars, int S, int H, int W, uint8_t* mask, cudaStream_t st);

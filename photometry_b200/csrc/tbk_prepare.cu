@@ -237,3 +237,33 @@ int tbk_launch_gather_stamps(const void* stack, int elem_bytes, int N, int H, in
 	if (e != cudaSuccess) { tbk_set_error("k_gather_stamps: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
 	return TBK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Catalog-driven star mask (extension; the reference's ``catalog`` argument is a TODO, photometry/backgrounds.py:64-65, 90):
+// pixel (row y, column x) is masked when (x - sx)^2 + (y - sy)^2 <= r^2 for some star (sx, sy, r).  One CTA per star walks the
+// star's bounding box; the mask is OR-ed into (several stars may cover a pixel: every writer stores the same 1).
+__global__ void __launch_bounds__(128) k_star_mask(const double* __restrict__ stars, int S, int H, int W, uint8_t* __restrict__ mask)
+{
+	const int s = blockIdx.x;
+	if (s >= S) return;
+	const double sx = stars[3 * s], sy = stars[3 * s + 1], r = stars[3 * s + 2];
+	if (!(r >= 0.0) || !(sx == sx) || !(sy == sy)) return;
+	const int x0 = max(0, (int)ceil(sx - r)), x1 = min(W - 1, (int)floor(sx + r));
+	const int y0 = max(0, (int)ceil(sy - r)), y1 = min(H - 1, (int)floor(sy + r));
+	if (x1 < x0 || y1 < y0) return;
+	const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
+	const double r2 = r * r;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		const int y = y0 + i / bw, x = x0 + i % bw;
+		const double dx = (double)x - sx, dy = (double)y - sy;
+		if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= r2) mask[(size_t)y * W + x] = 1;
+	}
+}
+
+int tbk_launch_star_mask(const double* stars, int S, int H, int W, uint8_t* mask, cudaStream_t st)
+{
+	k_star_mask<<<S, 128, 0, st>>>(stars, S, H, W, mask);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_star_mask: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}

@@ -551,3 +551,26 @@ def test_driver_gpu_products_equal_prepare_stack(tmp_path):
 		assert np.array_equal(np.asarray(hdf['backgrounds_pixels_used']).astype(np.uint8), res.backgrounds_pixels_used.cpu().numpy())
 		assert list(np.asarray(hdf['cadenceno'])) == [4700 + k for k in range(n)] and int(np.asarray(hdf['quality'])[2]) == 32
 		assert hdf.require_group('images').attrs['CAMERA'] == 1 and hdf.require_group('images').attrs['CADENCE'] == 1800
+
+
+# ---- catalog-driven star mask (extension) ------------------------------------------------------------
+def test_star_mask_equals_oracle_and_feeds_the_fit():
+	from photometry_b200.starmask import star_mask, star_radius
+	rng = np.random.default_rng(8)
+	H, W = 256, 320
+	cat = np.column_stack([rng.uniform(-5, W + 5, 400), rng.uniform(-5, H + 5, 400), rng.uniform(4, 16, 400)])
+	got = star_mask((H, W), cat).cpu().numpy().astype(bool)
+	ref = oracle.star_mask((H, W), cat)
+	assert np.array_equal(got, ref) and 0.02 < ref.mean() < 0.6
+	assert np.allclose(star_radius([10.0, 7.0, 20.0, 0.0]), [4.0, 4.0 * 10 ** 0.3, 1.5, 40.0])
+	assert np.array_equal(oracle.star_radius([10.0, 7.0, 20.0, 0.0]), star_radius([10.0, 7.0, 20.0, 0.0]))
+	# through the drop-in: fit_background(image, catalog) == oracle with the same mask as extra_mask
+	img = (300 + 20 * rng.standard_normal((H, W))).astype('float32')
+	for sx, sy, tm in cat[:60]:
+		if 0 <= sx < W and 0 <= sy < H:
+			img[int(sy), int(sx)] += 5e4 * 10 ** (-0.4 * (tm - 6))
+	bkg, mask = pb.fit_background(img, catalog=cat)
+	rb, rm = oracle.fit_background(img, extra_mask=ref)
+	assert np.array_equal(mask, rm) and in_tolerance(bkg, rb).all()
+	bkg0, mask0 = pb.fit_background(img)                 # default: the catalog is not used, as in the reference
+	assert not mask0.any() or mask0.sum() < mask.sum()
