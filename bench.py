@@ -327,10 +327,12 @@ def run_b200(args):
 		fit.fit(cube[a:b], meta_d[a * isz:b * isz], bkg_out=bkg[a:b], mask_out=mask[a:b], profile=prof)
 	ncalls = (n + chunk - 1) // chunk
 	dom = max((k for k in prof if k != 'misc'), key=lambda k: prof[k])
-	launches_per_call = {'tile_base': 1, 'tile_round': 3, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
+	# launches per tbk_fit_batch and class (3 rounds): zone statistics + queued bucketed fallback for the raw pixels; per round
+	# producer + finish + queued fallback for the residuals
+	launches_per_call = {'tile_base': 2, 'tile_round': 9, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
 	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
 	peak, peak_src = load_peaks()
-	# The fit is a chain of 25 kernel launches per batch and no single kernel dominates (the largest is < 30 % of
+	# The fit is a chain of ~32 kernel launches per batch and no single kernel dominates (the largest is < 30 % of
 	# the step), so the roofline is stated for the whole chain: algorithmic bytes of one tbk_fit_batch launch
 	# (37,748,736 B x FFIs per launch) over the summed device time of its kernels (CUDA events between the
 	# launches, tbk_fit_batch_profiled).  The dominant kernel is reported beside it with its share of the step.
@@ -340,7 +342,7 @@ def run_b200(args):
 	traffic = None
 	dom_traffic = None
 	try:
-		with open(os.path.join(ROOT, 'profiles', 'r01_ncu_fit_summary.json')) as fid:
+		with open(os.path.join(ROOT, 'profiles', 'r02_ncu_fit_summary.json')) as fid:
 			prof_json = json.load(fid)
 		traffic = prof_json['dram_bytes_per_ffi'] * min(chunk, n)
 		for kname, e in prof_json['kernels'].items():
@@ -348,11 +350,12 @@ def run_b200(args):
 				dom_traffic = (e['dram_read_bytes'] + e['dram_write_bytes']) / e['launches'] / prof_json['ffis_per_launch'] * min(chunk, n)
 	except (OSError, KeyError, ValueError, AttributeError, TypeError, ZeroDivisionError):
 		pass
-	roofline = {"bound": "hbm", "kernel": "tbk_fit_batch (chain of 25 launches; sum of kernel device times)",
+	launches_per_batch = launches // max(args.steps * ncalls, 1)
+	roofline = {"bound": "hbm", "kernel": f"tbk_fit_batch (chain of {launches_per_batch} launches; sum of kernel device times)",
 		"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-		"traffic_source": "profiles/r01_ncu_fit_summary.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum over the chain, scaled to this launch size)",
+		"traffic_source": "profiles/r02_ncu_fit_summary.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum over the chain, scaled to this launch size)",
 		"peak_source": peak_src, "launch_ms": launch_ms, "ffis_per_launch": min(chunk, n),
-		"limiter": "instruction issue / shared-memory atomics of the exact sigma-clip selection, not HBM (see DESIGN.md)",
+		"limiter": "instruction issue of the exact sigma-clip statistics and the KDE sweeps, not HBM (see DESIGN.md)",
 		"dominant_kernel": {"name": "k_" + dom, "share_of_step": prof[dom] / kern_total_ms, "launch_ms": dom_launch_ms,
 			"launches_per_batch": launches_per_call.get(dom, 1), "traffic": dom_traffic},
 		"kernel_shares": {k: round(v / kern_total_ms, 4) for k, v in prof.items()},

@@ -184,11 +184,13 @@ __device__ bool zone_iterate(TailsEach tails_each, const typename T::K* zone, co
 	};
 	double lo_run = -INFINITY, hi_run = INFINITY, lo_last = 0.0, hi_last = 0.0;
 	int n_prev = -1;
+	bool converged = false, nested_last = true;
+	double mean_c = 0.0, sd_c = 0.0, med_c = 0.0;       // statistics of the buffer at the last bound computation
 	for (int it = 0; it < 5; ++it) {
 		int c, below; double t1, t2;
 		tail_stats(lo_run, hi_run, c, below, t1, t2);
 		const int ni = nbulk + c;
-		if (ni == n_prev) break;                       // the previous clip removed nothing: its bounds are the last ones
+		if (ni == n_prev) { converged = true; break; }   // the previous clip removed nothing: its bounds are the last ones
 		const double m1 = (s1b + t1) / (double)ni;
 		const double sd = sqrt(fmax((s2b + t2) / (double)ni - m1 * m1, 0.0));
 		const int q = below + ((ni - 1) >> 1) - nZL;
@@ -196,11 +198,18 @@ __device__ bool zone_iterate(TailsEach tails_each, const typename T::K* zone, co
 		if (q < 0 || q + (two ? 1 : 0) >= nZ) return false;
 		const double med = zone_median(q, two);
 		lo_last = med - 3.0 * sd; hi_last = med + 3.0 * sd;
+		nested_last = lo_last >= lo_run && hi_last <= hi_run;
 		lo_run = fmax(lo_run, lo_last); hi_run = fmin(hi_run, hi_last);
 		if (lo_run > vA || hi_run < vB) return false;   // a bound entered the bulk
-		n_prev = ni;
+		n_prev = ni; mean_c = pivot + m1; sd_c = sd; med_c = med;
 	}
 	// ---- final statistics: ORIGINAL valid values inside the last bounds (lo_last <= lo_run <= vA, hi_last >= vB)
+	if (converged && nested_last) {
+		// the last clip removed nothing and its bounds lie inside the running range: the final set IS the buffer whose
+		// count / mean / median / std were computed with those bounds
+		out.nfin = n_prev; out.mean = mean_c; out.std = sd_c; out.med = med_c;
+		return true;
+	}
 	{
 		int c, below; double t1, t2;
 		tail_stats(lo_last, hi_last, c, below, t1, t2);

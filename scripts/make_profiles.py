@@ -57,7 +57,8 @@ for d in data:
 total_us = sum(e['time_us'] for e in kern.values())
 for e in kern.values():
 	e['share'] = e['time_us'] / total_us
-out = dict(source=f"ncu --set full --clock-control none --import-source on -k regex:^k_ -s 25 -c 25 python scripts/prof_run.py {nffi}: the 25 kernel launches of one tbk_fit_batch over {nffi} synthetic 2048x2048 TESS FFIs (cold-cache, serialised)",
+nl = sum(e['launches'] for e in kern.values())
+out = dict(source=f"ncu --set full --clock-control none --import-source on -k regex:^k_ -s {nl} -c {nl} python scripts/prof_run.py {nffi}: the {nl} kernel launches of one tbk_fit_batch over {nffi} synthetic 2048x2048 TESS FFIs (cold-cache, serialised)",
 	ffis_per_launch=nffi, kernels=kern, total_time_us=total_us,
 	dram_bytes_per_ffi=sum(e['dram_read_bytes'] + e['dram_write_bytes'] for e in kern.values()) / nffi, algorithmic_bytes_per_ffi=2048 * 2048 * 9)
 json.dump(out, open(os.path.join(prof, f'{rnd}_ncu_fit_summary.json'), 'w'), indent=1)

@@ -15,3 +15,14 @@ flags = res.pixel_flags.clone()
 mean = pb.background_shenanigans(res.images, res.sumimage, flags)
 torch.cuda.synchronize()
 print('ok', float(res.sumimage.nanmean()), float(mean.abs().max()))
+# IDW fill through the kd-tree (Mars columns excluded), star mask, image movement kernels
+mars = CASES['mars']()
+fitm = pb.BackgroundFitter(mars['images'].shape[1:], True, mars['camera'], mars['ccd'])
+bk, mk, st = fitm.fit(torch.from_numpy(mars['images']).cuda(), pb.meta_from_headers(mars['headers']))
+from photometry_b200.starmask import star_mask
+from photometry_b200.image_motion import ImageMovementKernel
+sm = star_mask((H, W), np.array([[10.5, 20.2, 8.0], [200.0, 100.0, 12.0], [-3.0, 5.0, 6.0]]))
+imk = ImageMovementKernel(res.images[0])
+kern = imk.calc_kernels(res.images[:3], number_of_iterations=20)
+torch.cuda.synchronize()
+print('ok2', int(fitm.status_to_numpy(st)[0]['n_excluded'][0]), int(sm.sum()), kern.shape)
