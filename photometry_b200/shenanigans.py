@@ -110,25 +110,19 @@ def cadence_to_row_slabs(ind, group=None):
 	dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=ind.device), group=group)
 	counts = [int(c.item()) for c in counts]
 	lo, hi = slab_bounds(H, world, rank)
+	# ONE all_to_all_single: the send buffer holds, rank after rank, this shard's rows of that rank's slab; the chunk
+	# received from rank r is cadence block r of the slab, which is contiguous in [numfiles, rows, W].
 	slab = torch.empty((sum(counts), hi - lo, W), dtype=ind.dtype, device=ind.device)
-	to_global = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
-	ops, keep = [], []
-	start = 0
+	send = torch.empty(n_local * H * W, dtype=ind.dtype, device=ind.device)
+	in_splits, out_splits, off = [], [], 0
 	for r in range(world):
 		rlo, rhi = slab_bounds(H, world, r)
-		dst_view = slab[start:start + counts[r]]
-		if r == rank:
-			dst_view.copy_(ind[:, lo:hi])
-		else:
-			if n_local and rhi > rlo:
-				send = ind[:, rlo:rhi].contiguous(); keep.append(send)
-				ops.append(dist.P2POp(dist.isend, send, to_global(r), group))
-			if counts[r] and hi > lo:
-				ops.append(dist.P2POp(dist.irecv, dst_view, to_global(r), group))
-		start += counts[r]
-	if ops:
-		for req in dist.batch_isend_irecv(ops):
-			req.wait()
+		m = n_local * (rhi - rlo) * W
+		if m:
+			send[off:off + m].view(n_local, rhi - rlo, W).copy_(ind[:, rlo:rhi])
+		in_splits.append(m); off += m
+		out_splits.append(counts[r] * (hi - lo) * W)
+	dist.all_to_all_single(slab.view(-1), send, out_splits, in_splits, group=group)
 	return slab
 
 
