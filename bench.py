@@ -63,8 +63,21 @@ class ClockSampler:
 
 	def __init__(self, index):
 		self.index = index
-		self.lines = []
+		self.lines = []            # (monotonic time of arrival, csv line)
 		self.proc = None
+		self.t0 = self.t1 = None
+
+	def wait_first(self, timeout=5.0):
+		"""nvidia-smi needs a few hundred ms to print its first sample: wait for it before the region of interest."""
+		end = time.monotonic() + timeout
+		while self.proc is not None and not self.lines and time.monotonic() < end:
+			time.sleep(0.02)
+
+	def mark_begin(self):
+		self.t0 = time.monotonic()
+
+	def mark_end(self):
+		self.t1 = time.monotonic()
 
 	def start(self):
 		try:
@@ -77,7 +90,7 @@ class ClockSampler:
 
 	def _read(self):
 		for line in self.proc.stdout:
-			self.lines.append(line.strip())
+			self.lines.append((time.monotonic(), line.strip()))
 
 	def stop(self):
 		if self.proc is None:
@@ -89,7 +102,9 @@ class ClockSampler:
 			self.proc.kill()
 		sm, mx, reasons = [], [], set()
 		names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-		for ln in self.lines:
+		# samples that arrived while the GPU was inside the marked region (a sample describes the ~100 ms before it)
+		lines = [ln for t, ln in self.lines if self.t0 is None or (t >= self.t0 and (self.t1 is None or t <= self.t1 + 0.1))]
+		for ln in lines:
 			f = [x.strip() for x in ln.split(',')]
 			if len(f) < 7:
 				continue
@@ -295,12 +310,15 @@ def run_b200(args):
 			dist.barrier()
 			torch.cuda.synchronize(dev)
 
-	for _ in range(args.warmup):
-		step()
-	barrier()
 	sampler = ClockSampler(local_rank)
 	if rank == 0:
 		sampler.start()
+	for _ in range(args.warmup):
+		step()
+	barrier()
+	if rank == 0:
+		sampler.wait_first()
+		sampler.mark_begin()
 	l0 = lib.tbk_launch_count()
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	e0.record()
@@ -310,7 +328,20 @@ def run_b200(args):
 	barrier()
 	launches = int(lib.tbk_launch_count() - l0)
 	ms = e0.elapsed_time(e1)
-	clocks = sampler.stop() if rank == 0 else None
+	clocks = None
+	if rank == 0:
+		sampler.mark_end()
+		window = "timed region"
+		if sum(1 for t, _ in sampler.lines if t >= sampler.t0) < 2 and world == 1:
+			# a timed region shorter than two 100-ms sampling periods: keep the same load running (untimed) for the sampler
+			end = time.monotonic() + 0.6
+			while time.monotonic() < end:
+				step()
+				torch.cuda.synchronize(dev)
+			sampler.mark_end()
+			window = "timed region + 0.6 s of the same load (untimed)"
+		clocks = sampler.stop()
+		clocks["window"] = window
 	if world > 1:
 		t = torch.tensor([ms], dtype=torch.float64, device=dev)
 		dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -43,7 +43,7 @@ struct tbk_plan {
 	PlanDev dev;
 	int device;
 	std::vector<void*> allocs;
-	int tile_kernel;   // TBK_TILE_KERNEL (development / cross-check switch): 0 = generic CTA-per-mesh kernels, 3 = bucketed kernels, 6 = zone kernels with the bucketed ones as fallback (default)
+	int tile_kernel;   // TBK_TILE_KERNEL (development / cross-check switch): 0 = generic CTA-per-mesh kernels, 3 = bucketed kernels, 6 = zone kernels with the bucketed ones as fallback (default), 7 = 6 with the raw mesh staged by TMA bulk copies (measured alternative)
 	std::map<cudaStream_t, TbkSide> sides;   // per caller stream (see TbkSide)
 	std::mutex mtx;
 };
@@ -173,7 +173,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 
 	tbk_plan* p = new tbk_plan();
 	p->device = device;
-	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 6; if (p->tile_kernel != 0 && p->tile_kernel != 3) p->tile_kernel = 6; }
+	{ const char* tk = getenv("TBK_TILE_KERNEL"); p->tile_kernel = tk ? (tk[0] - '0') : 6; if (p->tile_kernel != 0 && p->tile_kernel != 3 && p->tile_kernel != 7) p->tile_kernel = 6; }
 	PlanDev& P = p->dev;
 	memset(&P, 0, sizeof(P));
 	P.H = H; P.W = W; P.ny = H / TBK_TILE; P.nx = W / TBK_TILE; P.ntiles = P.ny * P.nx;

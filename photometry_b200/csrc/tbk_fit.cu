@@ -306,11 +306,25 @@ __device__ __forceinline__ void zb_p2(float x, uint32_t ex, uint32_t cut, uint32
 	}
 }
 
-template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Workspace ws,
+template <bool STAGED>
+__device__ __forceinline__ float4 zb_ld(const float* p)
+{
+	return STAGED ? *reinterpret_cast<const float4*>(p) : __ldg(reinterpret_cast<const float4*>(p));
+}
+// STAGED = true is the measured alternative (TBK_TILE_KERNEL=7): the 16 KB mesh is brought into shared memory by 64
+// TMA bulk row copies (cp.async.bulk + mbarrier, one barrier per warp) and both passes read it from there instead of
+// from global memory / L2.  The tile costs 16 KB per warp on top of the 9.75 KB of lists: 8 resident warps per SM
+// instead of 20 (DESIGN.md "Decisions recorded with numbers").
+struct ZbStage {
+	float px[ZB_WARPS][TBK_NPIX_TILE];
+	unsigned long long bar[ZB_WARPS];
+};
+template <bool HAS_EXTRA, bool STAGED>
+__global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
 {
 	__shared__ ZoneSmem<Zn32> smw[ZB_WARPS];
+	extern __shared__ __align__(128) unsigned char zb_dyn[];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int tile = blockIdx.x * ZB_WARPS + w, b = blockIdx.y;
 	if (tile >= P.ntiles) return;
@@ -320,13 +334,29 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Wor
 	const size_t tile0 = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE;
 	const size_t base = tile0 + (size_t)(lane >> 4) * P.W + ((lane & 15) << 2);
 	const size_t step = (size_t)2 * P.W;
+	// where the two passes read the pixels: global memory, or the staged tile (row stride 64)
+	const float* px0 = cube + base;
+	size_t pstep = step;
+	if (STAGED) {
+		ZbStage& stg = *reinterpret_cast<ZbStage*>(zb_dyn);
+		if (lane == 0) { tma_bar_init(&stg.bar[w], 1); tma_bar_expect(&stg.bar[w], (unsigned)(TBK_NPIX_TILE * sizeof(float))); }
+		__syncwarp();
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const int row = lane + 32 * h;
+			tma_load_1d(&stg.px[w][row * TBK_TILE], cube + tile0 + (size_t)row * P.W, (unsigned)(TBK_TILE * sizeof(float)), &stg.bar[w]);
+		}
+		px0 = &stg.px[w][(lane >> 4) * TBK_TILE + ((lane & 15) << 2)];
+		pstep = 2 * TBK_TILE;
+		tma_bar_wait(&stg.bar[w], 0u);
+	}
 	const uint32_t cut = __float_as_uint(P.flux_cutoff);
 	float* sbdst = ws.sbmin + ((size_t)b * P.ntiles + tile) * 64;
 	// manual excludes are mesh-uniform (the Mars boundary, column 1536, is a multiple of the mesh size): nothing is valid
 	if ((c.mars && tx * TBK_TILE >= 1536) || c.earth) {
 		uint32_t nz = 0u;
 		for (int i = 0; i < 32; ++i) {
-			const float4 r = __ldg(reinterpret_cast<const float4*>(cube + base + (size_t)i * step));
+			const float4 r = zb_ld<STAGED>(px0 + (size_t)i * pstep);
 			nz |= __float_as_uint(r.x + 0.0f) | __float_as_uint(r.y + 0.0f) | __float_as_uint(r.z + 0.0f) | __float_as_uint(r.w + 0.0f);
 			*reinterpret_cast<unsigned int*>(mask_out + base + (size_t)i * step) = 0x01010101u;
 		}
@@ -350,7 +380,8 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Wor
 		for (int t = 0; t < 2; ++t) {
 			const int idx = (lane * 131 + 17 + t * 2053) & (TBK_NPIX_TILE - 1);
 			const size_t off = tile0 + (size_t)(idx >> 6) * P.W + (idx & 63);
-			const uint32_t k = __float_as_uint(__ldg(cube + off) + 0.0f);
+			const float xs = STAGED ? reinterpret_cast<const ZbStage*>(zb_dyn)->px[w][idx] : __ldg(cube + off);
+			const uint32_t k = __float_as_uint(xs + 0.0f);
 			bool ok = k <= cut;
 			if (HAS_EXTRA) ok = ok && !__ldg(extra + off);
 			sk[t] = ok ? k : Zn32::padkey();
@@ -385,13 +416,13 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Wor
 	int nbad = 0, nA = 0, nM = 0, nC = 0;
 	double s1 = 0.0, s2 = 0.0;
 	float4 nx4[4]; uint32_t nex[4] = {0u, 0u, 0u, 0u};
-	const float* pc = cube + base;                  // this lane's pixels of the current band (bumped by 8 rows per band)
+	const float* pc = px0;                          // this lane's pixels of the current band (bumped by 8 rows per band)
 	const uint8_t* pe = HAS_EXTRA ? extra + base : nullptr;
 	uint8_t* pm = mask_out + base;
-	const size_t band = 4 * step;
+	const size_t band = 4 * step, pband = 4 * pstep;
 #pragma unroll
 	for (int h = 0; h < 4; ++h) {
-		nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+		nx4[h] = zb_ld<STAGED>(pc + h * pstep);
 		if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
 	}
 #pragma unroll 1
@@ -399,11 +430,11 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Wor
 		float4 r[4]; uint32_t exr[4];
 #pragma unroll
 		for (int h = 0; h < 4; ++h) { r[h] = nx4[h]; exr[h] = nex[h]; }
-		pc += band; if (HAS_EXTRA) pe += band;
+		pc += pband; if (HAS_EXTRA) pe += band;
 		if (a < 7) {
 #pragma unroll
 			for (int h = 0; h < 4; ++h) {
-				nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+				nx4[h] = zb_ld<STAGED>(pc + h * pstep);
 				if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
 			}
 		}
@@ -459,10 +490,10 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Wor
 			uint32_t zptr = zbase;
 			const uint32_t zend = zbase + 128u * ZN_ZCAP;
 			int nZL = 0;
-			pc = cube + base; if (HAS_EXTRA) pe = extra + base;
+			pc = px0; if (HAS_EXTRA) pe = extra + base;
 #pragma unroll
 			for (int h = 0; h < 4; ++h) {
-				nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+				nx4[h] = zb_ld<STAGED>(pc + h * pstep);
 				if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
 			}
 #pragma unroll 1
@@ -470,11 +501,11 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, 5) k_tile_base_z(PlanDev P, Wor
 				float4 r[4]; uint32_t exr[4];
 #pragma unroll
 				for (int h = 0; h < 4; ++h) { r[h] = nx4[h]; exr[h] = nex[h]; }
-				pc += band; if (HAS_EXTRA) pe += band;
+				pc += pband; if (HAS_EXTRA) pe += band;
 				if (a < 7) {
 #pragma unroll
 					for (int h = 0; h < 4; ++h) {
-						nx4[h] = __ldg(reinterpret_cast<const float4*>(pc + h * step));
+						nx4[h] = zb_ld<STAGED>(pc + h * pstep);
 						if (HAS_EXTRA) nex[h] = __ldg(reinterpret_cast<const unsigned int*>(pe + h * step));
 					}
 				}
@@ -1798,14 +1829,12 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 }
 
 #define ZF_WARPS 4
-#define ZF_TCAP 768
 #define ZF_ZCAP 512
 struct ZoneFinSmem {
-	double tails[ZF_TCAP];
 	unsigned long long zone[ZF_ZCAP];
 	uint32_t cnt[ZN_BINS];
 };
-__global__ void __launch_bounds__(32 * ZF_WARPS, 5) k_tile_round_fin(PlanDev P, Workspace ws, int round)
+__global__ void __launch_bounds__(32 * ZF_WARPS, 6) k_tile_round_fin(PlanDev P, Workspace ws, int round)
 {
 	__shared__ ZoneFinSmem smw[ZF_WARPS];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1817,24 +1846,14 @@ __global__ void __launch_bounds__(32 * ZF_WARPS, 5) k_tile_round_fin(PlanDev P, 
 	const double* gt = reinterpret_cast<const double*>(reinterpret_cast<const char*>(&rec) + sizeof(ZoneRec));
 	const double* gz = gt + 4 * ZR_TQ;
 	const int tq[4] = {rec.tq[0], rec.tq[1], rec.tq[2], rec.tq[3]}, zq[4] = {rec.zq[0], rec.zq[1], rec.zq[2], rec.zq[3]};
-	const int nT = tq[0] + tq[1] + tq[2] + tq[3], nZ = zq[0] + zq[1] + zq[2] + zq[3];
+	const int nZ = zq[0] + zq[1] + zq[2] + zq[3];
 	const double ZL = rec.ZL, ZH = rec.ZH;
 	const float zscale = (float)ZN_BINS / (float)(ZH - ZL) * 0.99999f;
 	TileStat st;
-	bool good = nT <= ZF_TCAP && nZ <= ZF_ZCAP;
-	if (good) {
-		// tails: the four quarters -> one dense list in shared memory (they are swept once per clip iteration)
-		int dstT = 0;
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			for (int i = lane; i < tq[q]; i += 32) sm.tails[dstT + i] = gt[q * ZR_TQ + i];
-			dstT += tq[q];
-		}
-		__syncwarp();
-		const int one_t[1] = {nT};
-		good = zone_finish_seg<Zn64, 1, 4>(sm.tails, 0, one_t, gz, ZR_ZQ, zq, sm.zone, sm.cnt, lane,
-			rec.n, rec.nA, rec.nB, rec.nZL, rec.s1, rec.s2, rec.pivot, rec.A, rec.B, ZL, zscale, st);
-	}
+	bool good = nZ <= ZF_ZCAP;
+	// the tails go from the four quarters (global memory, L2) straight into the registers of the clip sweeps
+	if (good) good = zone_finish_seg<Zn64, 4, 4>(gt, ZR_TQ, tq, gz, ZR_ZQ, zq, sm.zone, sm.cnt, lane,
+		rec.n, rec.nA, rec.nB, rec.nZL, rec.s1, rec.s2, rec.pivot, rec.A, rec.B, ZL, zscale, st);
 	if (lane == 0) {
 		if (good) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
 		else ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot;
@@ -2246,8 +2265,19 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else {
 		const dim3 gz((P.ntiles + ZB_WARPS - 1) / ZB_WARPS, B);
-		if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
-		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
+		if (tile_kernel == 7) {
+			// measured alternative: mesh staged in shared memory by TMA bulk copies
+			static bool attr_set = false;
+			if (!attr_set) {
+				cudaFuncSetAttribute(k_tile_base_z<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
+				cudaFuncSetAttribute(k_tile_base_z<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
+				attr_set = true;
+			}
+			if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, true><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask)));
+			else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, true><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask)));
+		}
+		else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
+		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
 		// the queued meshes (bucketed statistics) are only needed by k_mesh_finalize: side stream, joined before round 0's
 		cudaStream_t fs = st;
 		if (side && !prof) { fs = side->stream; cudaEventRecord(side->fork, st); cudaStreamWaitEvent(fs, side->fork, 0); base_forked = true; }

@@ -32,6 +32,8 @@ struct Zn32 : TwF32 {
 	__device__ static __forceinline__ K key_of(Raw r) { return r; }
 	__device__ static __forceinline__ double rval(Raw r) { return (double)__uint_as_float(r); }
 	__device__ static __forceinline__ float offs(Raw r, Raw zl) { return (float)(r - zl); }
+	static constexpr bool kStoreD = true;     // the clip sweeps keep value - pivot (float64) next to the 32-bit raw value
+	__device__ static __forceinline__ Raw padraw() { return 0xFFFFFFFFu; }   // compares false against every range
 	// inclusive value range [lo, hi] as raw thresholds: raw >= tlo && raw <= thi  <=>  lo <= value <= hi
 	struct Range { Raw tlo, thi; };
 	__device__ static __forceinline__ Range range(double lo, double hi)
@@ -47,6 +49,8 @@ struct Zn64 : TwF64 {
 	__device__ static __forceinline__ K key_of(Raw r) { return dkey(r); }
 	__device__ static __forceinline__ double rval(Raw r) { return r; }
 	__device__ static __forceinline__ float offs(Raw r, Raw zl) { return (float)(r - zl); }
+	static constexpr bool kStoreD = false;
+	__device__ static __forceinline__ Raw padraw() { return nan_d(); }
 	struct Range { Raw tlo, thi; };
 	__device__ static __forceinline__ Range range(double lo, double hi) { Range r; r.tlo = lo; r.thi = hi; return r; }
 };
@@ -109,10 +113,12 @@ __device__ __forceinline__ void zone_range(const ZonePlan& zp, int n, int nA, in
 }
 
 // ---- pieces of the finish phase (one warp) ----------------------------------------------------------------------
+#define ZN_TREG 12        // tail elements per lane held in registers across the clip iterations (more: re-read from memory)
+#define ZN_LANEMAX 64     // a lane never sorts more zone keys than this (4 bins); fuller bins send the mesh to the bucketed path
 
 // Exclusive scan of the ZN_BINS bin counts in cnt[] (4 consecutive bins per lane): cnt becomes the bin starts, bend[]
-// (registers) the ends of this lane's bins.
-__device__ __forceinline__ void zone_scan_bins(uint32_t* cnt, int lane, uint32_t (&bend)[ZN_BINS / 32])
+// (registers) the ends of this lane's bins.  Returns the start of the lane's first bin.
+__device__ __forceinline__ uint32_t zone_scan_bins(uint32_t* cnt, int lane, uint32_t (&bend)[ZN_BINS / 32])
 {
 	uint32_t c[ZN_BINS / 32], tot = 0;
 #pragma unroll
@@ -121,109 +127,112 @@ __device__ __forceinline__ void zone_scan_bins(uint32_t* cnt, int lane, uint32_t
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
 	uint32_t run = inc - tot;
+	const uint32_t start0 = run;
 #pragma unroll
 	for (int j = 0; j < ZN_BINS / 32; ++j) { cnt[lane * (ZN_BINS / 32) + j] = run; run += c[j]; bend[j] = run; }
+	return start0;
 }
 
-// The clip iterations and the final statistics.  ``zone``: the nZ zone keys sorted by bin (shared memory), ``bend``: the
-// bin ends (registers, 4 bins per lane); ``tails_each(f)`` calls f(raw) for every tail element this lane is responsible for
-// (all lanes together cover each of the nA + nB tail elements once).  vA / vB: smallest / largest value a bulk element
-// can have.  Returns false when the lists cannot answer (the caller queues the mesh for the bucketed path).
-template <typename T, typename TailsEach>
-__device__ bool zone_iterate(TailsEach tails_each, const typename T::K* zone, const uint32_t (&bend)[ZN_BINS / 32], int lane,
+// The keys are grouped by bin; every lane insertion-sorts the keys of its own 4 consecutive bins (a handful), after which
+// zone[] is sorted as a whole and the key of a rank is a single load.
+template <typename K>
+__device__ __forceinline__ bool zone_sort_bins(K* zone, uint32_t s, uint32_t e)
+{
+	const bool ok = e - s <= (uint32_t)ZN_LANEMAX;
+	if (ok) {
+		for (uint32_t i = s + 1; i < e; ++i) {
+			const K v = zone[i];
+			uint32_t p = i;
+			while (p > s && zone[p - 1] > v) { zone[p] = zone[p - 1]; --p; }
+			zone[p] = v;
+		}
+	}
+	return !__any_sync(0xffffffffu, !ok);
+}
+
+// The clip iterations and the final statistics.  ``zone``: the nZ zone keys, sorted (shared memory); ``tail_at(i)``: tail
+// element i of the nA + nB (any order).  The first 32 * ZN_TREG tails live in registers for all sweeps.  vA / vB: smallest /
+// largest value a bulk element can have.  Returns false when the lists cannot answer (the caller queues the mesh for the
+// bucketed path).
+template <typename T, typename TailAt>
+__device__ bool zone_iterate(TailAt tail_at, const typename T::K* zone, int lane,
 	int n, int nA, int nB, int nZL, int nZ, double s1b, double s2b, double pivot, double vA, double vB, TileStat& out)
 {
 	typedef typename T::K K;
 	typedef typename T::Raw Raw;
 	const int nbulk = n - nA - nB, nT = nA + nB;
-	// key of zone rank r: bin lookup over the ends, then the ranks inside the bin by counting (a bin holds a few keys)
-	auto zone_key = [&](uint32_t r) -> K {
-		const unsigned m4 = __ballot_sync(0xffffffffu, bend[ZN_BINS / 32 - 1] > r);
-		const int g = __ffs(m4) - 1;
-		uint32_t bs = __shfl_sync(0xffffffffu, bend[ZN_BINS / 32 - 1], max(g - 1, 0));
-		if (g == 0) bs = 0u;
-		uint32_t be = 0u;
-		bool found = false;
+	Raw tr[ZN_TREG];
+	double td[T::kStoreD ? ZN_TREG : 1];
 #pragma unroll
-		for (int j = 0; j < ZN_BINS / 32; ++j) {
-			const uint32_t ej = __shfl_sync(0xffffffffu, bend[j], g);
-			if (!found) { if (ej > r) { be = ej; found = true; } else bs = ej; }
+	for (int j = 0; j < ZN_TREG; ++j) {
+		tr[j] = T::padraw();
+		if (j * 32 < nT) {
+			const int i = j * 32 + lane;
+			if (i < nT) tr[j] = tail_at(i);
 		}
-		const uint32_t m = be - bs;
-		if (m > 32u) {   // many equal / near-equal keys: exact radix selection
-			K k1, k2;
-			tw_select_in_span<T>(zone, bs, be, r - bs, false, lane, k1, k2);
-			return k1;
-		}
-		const K mine = ((uint32_t)lane < m) ? zone[bs + lane] : T::padkey();
-		uint32_t rank = 0u;
-		for (uint32_t j = 0; j < m; ++j) {
-			const K kj = __shfl_sync(0xffffffffu, mine, (int)j);
-			rank += (kj < mine || (kj == mine && j < (uint32_t)lane)) ? 1u : 0u;
-		}
-		const unsigned hit = __ballot_sync(0xffffffffu, (uint32_t)lane < m && rank == r - bs);
-		return __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
-	};
+		if (T::kStoreD) td[j] = T::rval(tr[j]) - pivot;
+	}
 	auto zone_median = [&](int q, bool two) -> double {
-		const K k1 = zone_key((uint32_t)q);
-		const K k2 = two ? zone_key((uint32_t)q + 1u) : k1;
+		const K k1 = zone[q];
+		const K k2 = two ? zone[q + 1] : k1;
 		return 0.5 * (T::val(k1) + T::val(k2));
 	};
 	// statistics of { bulk } + { tails inside [lo, hi] }; ``below`` = tails under lo
 	auto tail_stats = [&](double lo, double hi, int& cnt, int& below, double& t1, double& t2) {
 		int c = 0, bl = 0; double a1 = 0.0, a2 = 0.0;
 		const typename T::Range rg = T::range(lo, hi);
-		tails_each([&](Raw r) {
+#pragma unroll
+		for (int j = 0; j < ZN_TREG; ++j) {
+			if (j * 32 < nT) {   // warp-uniform; padded slots compare false on both tests
+				const Raw r = tr[j];
+				const double d = T::kStoreD ? td[T::kStoreD ? j : 0] : T::rval(r) - pivot;
+				const bool lw = r < rg.tlo, in = !lw && r <= rg.thi;
+				bl += lw ? 1 : 0; c += in ? 1 : 0;
+				if (in) { a1 += d; a2 = fma(d, d, a2); }
+			}
+		}
+		for (int i = ZN_TREG * 32 + lane; i < nT; i += 32) {
+			const Raw r = tail_at(i);
 			const double d = T::rval(r) - pivot;
 			if (r < rg.tlo) ++bl;
 			else if (r <= rg.thi) { ++c; a1 += d; a2 = fma(d, d, a2); }
-		});
+		}
 		cnt = __reduce_add_sync(0xffffffffu, c); below = __reduce_add_sync(0xffffffffu, bl);
 		t1 = 0.0; t2 = 0.0;
 		if (nT) { t1 = warp_sum_d(a1); t2 = warp_sum_d(a2); }
 	};
 	double lo_run = -INFINITY, hi_run = INFINITY, lo_last = 0.0, hi_last = 0.0;
 	int n_prev = -1;
-	bool converged = false, nested_last = true;
+	bool nested_last = true;
 	double mean_c = 0.0, sd_c = 0.0, med_c = 0.0;       // statistics of the buffer at the last bound computation
-	for (int it = 0; it < 5; ++it) {
+#pragma unroll 1
+	for (int it = 0; it < 6; ++it) {
+		// it < 5: a clip iteration on the running bounds.  it == 5 (reached only without the shortcut below): the final
+		// statistics of the ORIGINAL valid values inside the last bounds (lo_last <= lo_run <= vA, hi_last >= vB).
+		const bool fin = it == 5;
 		int c, below; double t1, t2;
-		tail_stats(lo_run, hi_run, c, below, t1, t2);
+		tail_stats(fin ? lo_last : lo_run, fin ? hi_last : hi_run, c, below, t1, t2);
 		const int ni = nbulk + c;
-		if (ni == n_prev) { converged = true; break; }   // the previous clip removed nothing: its bounds are the last ones
+		if (!fin && ni == n_prev) {
+			// the previous clip removed nothing: its bounds are the last ones.  When they also lie inside the running range the
+			// final set IS the buffer whose count / mean / median / std were just computed with those bounds
+			if (nested_last) { out.nfin = n_prev; out.mean = mean_c; out.std = sd_c; out.med = med_c; return true; }
+			it = 4; continue;
+		}
 		const double m1 = (s1b + t1) / (double)ni;
 		const double sd = sqrt(fmax((s2b + t2) / (double)ni - m1 * m1, 0.0));
 		const int q = below + ((ni - 1) >> 1) - nZL;
 		const bool two = (ni & 1) == 0;
 		if (q < 0 || q + (two ? 1 : 0) >= nZ) return false;
 		const double med = zone_median(q, two);
+		if (fin) { out.nfin = ni; out.mean = pivot + m1; out.std = sd; out.med = med; return true; }
 		lo_last = med - 3.0 * sd; hi_last = med + 3.0 * sd;
 		nested_last = lo_last >= lo_run && hi_last <= hi_run;
 		lo_run = fmax(lo_run, lo_last); hi_run = fmin(hi_run, hi_last);
 		if (lo_run > vA || hi_run < vB) return false;   // a bound entered the bulk
 		n_prev = ni; mean_c = pivot + m1; sd_c = sd; med_c = med;
 	}
-	// ---- final statistics: ORIGINAL valid values inside the last bounds (lo_last <= lo_run <= vA, hi_last >= vB)
-	if (converged && nested_last) {
-		// the last clip removed nothing and its bounds lie inside the running range: the final set IS the buffer whose
-		// count / mean / median / std were computed with those bounds
-		out.nfin = n_prev; out.mean = mean_c; out.std = sd_c; out.med = med_c;
-		return true;
-	}
-	{
-		int c, below; double t1, t2;
-		tail_stats(lo_last, hi_last, c, below, t1, t2);
-		const int nf = nbulk + c;
-		const double m1 = (s1b + t1) / (double)nf;
-		const int q = below + ((nf - 1) >> 1) - nZL;
-		const bool two = (nf & 1) == 0;
-		if (q < 0 || q + (two ? 1 : 0) >= nZ) return false;
-		out.nfin = nf;
-		out.mean = pivot + m1;
-		out.std = sqrt(fmax((s2b + t2) / (double)nf - m1 * m1, 0.0));
-		out.med = zone_median(q, two);
-	}
-	return true;
+	return false;   // not reached
 }
 
 // Finish from per-lane lists in shared memory (the fused raw-pixel kernel).  tcnt / zcnt: this lane's list lengths;
@@ -285,7 +294,7 @@ __device__ bool zone_finish(ZoneSmem<T>& sm, int lane, int n, int nA, int nB, in
 			}
 		}
 		__syncwarp();
-		zone_scan_bins(sm.cnt, lane, bend);
+		const uint32_t start0 = zone_scan_bins(sm.cnt, lane, bend);
 		__syncwarp();
 #pragma unroll
 		for (int g8 = 0; g8 < ZN_ZCAP / 8; ++g8) {
@@ -298,10 +307,11 @@ __device__ bool zone_finish(ZoneSmem<T>& sm, int lane, int n, int nA, int nB, in
 			}
 		}
 		__syncwarp();
+		if (!zone_sort_bins(sm.zone, start0, bend[ZN_BINS / 32 - 1])) return false;
+		__syncwarp();
 	}
 	const Raw* tl = sm.tails;
-	auto tails_each = [&](auto f) { for (int i = lane; i < nT; i += 32) f(tl[i]); };
-	return zone_iterate<T>(tails_each, sm.zone, bend, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out);
+	return zone_iterate<T>([&](int i) { return tl[i]; }, sm.zone, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out);
 }
 
 // Finish from lists that are not per-lane: tails in TSEG segments of capacity tcap with tq[s] entries, zone elements in
@@ -331,13 +341,18 @@ __device__ bool zone_finish_seg(const typename T::Raw* gt, int tcap, const int (
 	};
 	zone_each([&](Raw r) { atomicAdd(&cnt[min(ZN_BINS - 1, (int)(T::offs(r, zl) * zscale))], 1u); });
 	__syncwarp();
-	zone_scan_bins(cnt, lane, bend);
+	const uint32_t start0 = zone_scan_bins(cnt, lane, bend);
 	__syncwarp();
 	zone_each([&](Raw r) { zone[atomicAdd(&cnt[min(ZN_BINS - 1, (int)(T::offs(r, zl) * zscale))], 1u)] = T::key_of(r); });
 	__syncwarp();
-	auto tails_each = [&](auto f) {
+	if (!zone_sort_bins(zone, start0, bend[ZN_BINS / 32 - 1])) return false;
+	__syncwarp();
+	// tail element i of the dense order "segment 0, segment 1, ..."
+	auto tail_at = [&](int i) -> Raw {
+		int s = 0;
 #pragma unroll
-		for (int s = 0; s < TSEG; ++s) for (int i = lane; i < tq[s]; i += 32) f(gt[s * tcap + i]);
+		for (int t = 0; t < TSEG - 1; ++t) { if (s == t && i >= tq[t]) { i -= tq[t]; s = t + 1; } }
+		return gt[s * tcap + i];
 	};
-	return zone_iterate<T>(tails_each, zone, bend, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out);
+	return zone_iterate<T>(tail_at, zone, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out);
 }

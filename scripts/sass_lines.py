@@ -41,6 +41,18 @@ for l in lines[start + 1:]:
 		loc[int(m.group(1), 16)] = (tuple(chain), m.group(2).strip())
 		cont = False
 
+if args.csv == '-':   # static mode: SASS instructions per source line (code size)
+	agg = collections.Counter()
+	for off, (ch, op) in loc.items():
+		ch = ch or ('?',)
+		if args.under and args.under not in ch:
+			continue
+		agg[ch[0] if args.depth < 0 else ch[max(len(ch) - 1 - args.depth, 0)]] += 1
+	print(f"{sum(agg.values())} SASS instructions")
+	for k, n in agg.most_common(args.top):
+		print(f"{k:34s} {n:6d}")
+	sys.exit(0)
+
 # 2. csv rows of the requested launch
 txt = open(args.csv).read()
 blocks = re.split(r'(?m)^"Kernel Name",', txt)[1:]

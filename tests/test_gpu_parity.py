@@ -257,7 +257,7 @@ def test_full_size_properties(full_stack):
 
 
 # ---- independent implementations agree --------------------------------------------------------
-VARIANTS = ('0', '3', '6')
+VARIANTS = ('0', '3', '6', '7')
 
 
 def test_kernel_variants_agree(monkeypatch):
