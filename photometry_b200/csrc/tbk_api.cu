@@ -1,5 +1,6 @@
 // tbk_api.cu -- C ABI (include/tbk.h): plan construction (static geometry tables) and entry points.
 #include <cstdarg>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -187,6 +188,8 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	std::vector<unsigned> ringtile_ent;
 	std::vector<double> nonflat_r;
 	std::vector<double2> nonflat_rr;
+	std::vector<double> nonflat_uj;
+	std::vector<int> nonflat_jlo;
 	if (P.use_radial) {
 		// backgrounds.py:145-154
 		std::vector<double> r((size_t)H * W);
@@ -270,6 +273,38 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 			}
 			nonflat_rr[k] = make_double2(lo, hi);
 		}
+		// Static part of the Taylor-piece evaluation of the radial profile (RadialTab, tbk_common.cuh): the piece a pixel
+		// falls into and its offset from the piece centre do not depend on the FFI.  Per pixel one float64 = the offset u
+		// with the low 6 mantissa bits replaced by the piece index relative to the first piece of the mesh (|du| < 2^-46 |u|);
+		// 62 / 63 mark pixels below the first / at or beyond the last ring centre (the spline is clamped there, ext=3).
+		nonflat_uj.assign((size_t)nonflat.size() * TBK_NPIX_TILE, 0.0);
+		nonflat_jlo.assign(nonflat.size(), 0);
+		{
+			const int nsub = TBK_RSUB * std::max(nrings - 1, 1);
+			const double hsub = radial_pixel_step / (double)TBK_RSUB, inv_h = (double)TBK_RSUB / radial_pixel_step;
+			const double clast = c0 + (double)(nrings - 1) * radial_pixel_step;
+			auto piece = [&](double v) { return std::max(0, std::min(nsub - 1, (int)((v - c0) * inv_h))); };
+			for (size_t k = 0; k < nonflat.size(); ++k) {
+				const double* rk = &nonflat_r[k * TBK_NPIX_TILE];
+				int jmin = INT_MAX, jmax = -1;
+				for (int e = 0; e < TBK_NPIX_TILE; ++e)
+					if (rk[e] >= c0 && rk[e] < clast) { const int j = piece(rk[e]); jmin = std::min(jmin, j); jmax = std::max(jmax, j); }
+				if (jmax < 0) jmin = jmax = 0;
+				nonflat_jlo[k] = (jmax - jmin < TBK_RTAB_ROWS) ? jmin : -1;   // -1: the mesh sees too many pieces, bucketed path
+				for (int e = 0; e < TBK_NPIX_TILE; ++e) {
+					unsigned long long bits;
+					if (rk[e] < c0) bits = 62ull;
+					else if (!(rk[e] < clast)) bits = 63ull;
+					else {
+						const int j = piece(rk[e]);
+						const double u = rk[e] - (c0 + ((double)j + 0.5) * hsub);
+						std::memcpy(&bits, &u, 8);
+						bits = (bits & ~63ull) | (unsigned long long)std::min(j - jmin, TBK_RTAB_ROWS - 1);
+					}
+					std::memcpy(&nonflat_uj[k * TBK_NPIX_TILE + e], &bits, 8);
+				}
+			}
+		}
 	}
 	// cubic B-spline weights per sub-tile phase (scipy ni_interpolation.c, order 3):
 	// output o samples u = (o + 0.5)/64 - 0.5; x = u - floor(u)
@@ -299,11 +334,15 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 		CUDA_TRY(cudaMemset(d, 0, words * sizeof(uint32_t)));
 		P.idw_cache = (uint32_t*)d;
 	}
+	// rings by decreasing sample count: the KDE grid starts its longest CTAs first, so the tail of the launch is short work
+	std::vector<int> ring_order(std::max(P.nrings, 1), 0);
+	for (int k = 0; k < P.nrings; ++k) ring_order[k] = k;
+	if (P.nrings > 0) std::stable_sort(ring_order.begin(), ring_order.end(), [&](int a, int b) { return ring_ptr[a + 1] - ring_ptr[a] > ring_ptr[b + 1] - ring_ptr[b]; });
 	int rc;
-	if ((rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
+	if ((rc = upload(p, ring_order, &P.ring_order)) || (rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
 		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
 		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle)) ||
-		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, nonflat_rr, &P.nonflat_rr)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
+		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, nonflat_rr, &P.nonflat_rr)) || (rc = upload(p, nonflat_uj, &P.nonflat_uj)) || (rc = upload(p, nonflat_jlo, &P.nonflat_jlo)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
 		tbk_plan_destroy(p);
 		return rc;
 	}

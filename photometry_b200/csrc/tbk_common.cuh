@@ -27,11 +27,14 @@ struct PlanDev {
 	int n_nonflat;              // tiles with max(r) > first ring centre
 	// device tables
 	const int* ring_ptr;        // [nrings + 1] CSR offsets into ring_pix
+	const int* ring_order;      // [nrings] ring ids by decreasing pixel count (launch order of the KDE CTAs)
 	const int* ring_pix;        // [nringpix] (y << 16) | x, row-major within a ring
 	const int* nonflat_tiles;   // [n_nonflat] tile ids
 	const int* tile_slot;       // [ntiles] index into nonflat list or -1 (flat tile)
 	const double* nonflat_r;    // [n_nonflat][64*64] pixel radius of the non-flat meshes (static, bit-equal to pixel_radius)
 	const double2* nonflat_rr;  // [n_nonflat] (min, max) of that radius over the mesh
+	const double* nonflat_uj;   // [n_nonflat][64*64] offset from the Taylor-piece centre | local piece index (see radial_tab_eval_uj)
+	const int* nonflat_jlo;     // [n_nonflat] first Taylor piece the mesh can see (-1: more than TBK_RTAB_ROWS pieces)
 	int n_ringtiles;            // meshes that contain at least one ring pixel
 	const int* ringtile_id;     // [n_ringtiles] mesh id
 	const int* ringtile_ptr;    // [n_ringtiles + 1] CSR offsets into ringtile_ent
@@ -195,6 +198,7 @@ __device__ __forceinline__ double clamp_d(double v, double lo, double hi)
 // zeropoint already subtracted from b_0, and u0:  radial(t) = b0 + u (b1 + u (b2 + ... + u b6)).  The truncated term is
 // below 1e-15 of the value for any profile the ring statistic can produce (|g'| ~ 1e-3 / px).
 #define TBK_RSUB 8
+#define TBK_RTAB_ROWS 56   // pieces one mesh can see (64 px diagonal = 91 px of radius < 56 pieces of step / 8 >= 1.75 px)
 struct RadialTab {
 	const double* rows;     // [nsub][8]: b0 - zp, b1 .. b6, u0
 	double x0, xlast, center0, inv_h;
@@ -219,6 +223,20 @@ __device__ __forceinline__ double radial_tab_eval_s(const RadialTab& t, const do
 	const double2 c01 = row[0], c23 = row[1], c45 = row[2], c6u = row[3];
 	const double u = tc - c6u.y;
 	return fma(u, fma(u, fma(u, fma(u, fma(u, fma(u, c6u.x, c45.y), c45.x), c23.y), c23.x), c01.y), c01.x);
+}
+// The evaluation from the static per-pixel word of PlanDev::nonflat_uj (offset from the piece centre with the local piece
+// index in the low 6 mantissa bits; 62 / 63 = clamped below / above): no clamp, no index arithmetic, no radius.
+//   j0 / j1: pieces [j0, j1) lie inside [x0, xlast] of this FFI's spline; cflat / clast: the profile at x0 / xlast.
+__device__ __forceinline__ int radial_tab_j0(const RadialTab& t) { return (int)((t.x0 - t.center0) * t.inv_h + 0.5); }
+__device__ __forceinline__ int radial_tab_j1(const RadialTab& t) { return (int)((t.xlast - t.center0) * t.inv_h + 0.5); }
+__device__ __forceinline__ double radial_tab_eval_uj(const double* srows, int jlo, int j0, int j1, double cflat, double clast, double uj)
+{
+	const int jl = (int)((unsigned long long)__double_as_longlong(uj) & 63ull);
+	const int ja = jlo + jl;
+	const double2* row = reinterpret_cast<const double2*>(srows + TBK_RROW * min(jl, TBK_RTAB_ROWS - 1));
+	const double2 c01 = row[0], c23 = row[1], c45 = row[2], c6u = row[3];
+	const double v = fma(uj, fma(uj, fma(uj, fma(uj, fma(uj, fma(uj, c6u.x, c45.y), c45.x), c23.y), c23.x), c01.y), c01.x);
+	return (jl == 62 || ja < j0) ? cflat : ((jl == 63 || ja >= j1) ? clast : v);
 }
 __device__ __forceinline__ double radial_tab_eval(const RadialTab& t, double r)
 {

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Wo
 //   bulk   = kA <= kv <= kA + spanAB:  s1 += x - pivot, s2 += (x - pivot)^2  (float64; a non-bulk pixel enters as the
 //            pivot itself -- the pivot is a float32 value -- i.e. as an exact zero, which keeps the float64 adds unpredicated)
 //   tail   = valid && !bulk: appended to this lane's list (pointer tptr, stride 128 B, not stored beyond tend)
-//   nA    += kv < kA;  nM += kv < kM;  nC += kC <= kv <= kC + spanC
+//   nA    += kv < kA;  nM += kv < kM;  every fourth pixel: nC += 4 * (kC <= kv <= kC + spanC)
 template <int Q, bool HAS_EXTRA>
 __device__ __forceinline__ void zb_p1(float x, uint32_t ex, uint32_t cut, uint32_t kA, uint32_t spanAB, uint32_t kM, double pivot,
 	uint32_t& m, uint32_t& smin, int& nA, int& nM, double& s1, double& s2, uint32_t& tptr, uint32_t tend, float pivot_f,
@@ -241,11 +241,8 @@ __device__ __forceinline__ void zb_p1(float x, uint32_t ex, uint32_t cut, uint32
 		"setp.le.u32 pbulk, t, %13;\n\t" \
 		"setp.lt.u32 plow, kv, %12;\n\t" \
 		"setp.lt.u32 pm, kv, %14;\n\t" \
-		"sub.u32 t, kv, %18;\n\t" \
-		"setp.le.u32 pc, t, %19;\n\t" \
 		"@plow add.s32 %2, %2, 1;\n\t" \
 		"@pm add.s32 %3, %3, 1;\n\t" \
-		"@pc add.s32 %7, %7, 1;\n\t" \
 		"selp.f32 xm, %9, %17, pbulk;\n\t" \
 		"cvt.f64.f32 d, xm;\n\t" \
 		"sub.f64 d, d, %15;\n\t" \
@@ -256,7 +253,20 @@ __device__ __forceinline__ void zb_p1(float x, uint32_t ex, uint32_t cut, uint32
 		"@pst st.shared.u32 [%6], kv;\n\t" \
 		"@pt add.u32 %6, %6, 128;\n\t" \
 		"@!pok or.b32 %0, %0, %8;\n\t"
-	if (HAS_EXTRA)
+	// the centre count nC only sizes the zone (local density), so every fourth pixel is enough for it
+#define ZB_P1_NC \
+		"sub.u32 t, kv, %18;\n\t" \
+		"setp.le.u32 pc, t, %19;\n\t" \
+		"@pc add.s32 %7, %7, 4;\n\t"
+	if (HAS_EXTRA && Q == 0)
+		asm volatile("{\n\t" ZB_P1_HEAD "setp.eq.and.u32 pok, %10, 0, pok;\n\t" ZB_P1_TAIL ZB_P1_NC "}"
+			: "+r"(m), "+r"(smin), "+r"(nA), "+r"(nM), "+d"(s1), "+d"(s2), "+r"(tptr), "+r"(nC)
+			: "n"(1u << (8 * Q)), "f"(x), "r"(ex), "r"(cut), "r"(kA), "r"(spanAB), "r"(kM), "d"(pivot), "r"(tend), "f"(pivot_f), "r"(kC), "r"(spanC) : "memory");
+	else if (Q == 0)
+		asm volatile("{\n\t" ZB_P1_HEAD ZB_P1_TAIL ZB_P1_NC "}"
+			: "+r"(m), "+r"(smin), "+r"(nA), "+r"(nM), "+d"(s1), "+d"(s2), "+r"(tptr), "+r"(nC)
+			: "n"(1u << (8 * Q)), "f"(x), "r"(ex), "r"(cut), "r"(kA), "r"(spanAB), "r"(kM), "d"(pivot), "r"(tend), "f"(pivot_f), "r"(kC), "r"(spanC) : "memory");
+	else if (HAS_EXTRA)
 		asm volatile("{\n\t" ZB_P1_HEAD "setp.eq.and.u32 pok, %10, 0, pok;\n\t" ZB_P1_TAIL "}"
 			: "+r"(m), "+r"(smin), "+r"(nA), "+r"(nM), "+d"(s1), "+d"(s2), "+r"(tptr), "+r"(nC)
 			: "n"(1u << (8 * Q)), "f"(x), "r"(ex), "r"(cut), "r"(kA), "r"(spanAB), "r"(kM), "d"(pivot), "r"(tend), "f"(pivot_f), "r"(kC), "r"(spanC) : "memory");
@@ -479,7 +489,7 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 		const int nB = nT - nA;
 		s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
 		double ZL, ZH;
-		zone_range(zp, n, nA, nB, nM, nC, ZL, ZH);
+		zone_range(zp, n, nA, nB, nM, nC, ZL, ZH, true);
 		uint32_t kZL = max(Zn32::key_ceil(ZL), kA), kZH = 0u;
 		good = Zn32::key_floor(ZH, kZH);
 		kZH = min(kZH, kB);
@@ -956,7 +966,9 @@ __global__ void __launch_bounds__(TBK_KDE_NT, 1024 / TBK_KDE_NT) k_ring_kde(Plan
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	KdeSmem& sm = *reinterpret_cast<KdeSmem*>(smraw);
-	const int ring = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+	// grid (B, nrings): the block index runs over the FFIs first, so the launch works through the rings from the longest to
+	// the shortest (ring_order) and ends on short CTAs
+	const int ring = P.ring_order[blockIdx.y], b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 	const FfiCtl& c = ws.ctl[b];
 	if (c.all_masked || c.no_good_mesh) return;
 	const int lo = P.ring_ptr[ring], hi = P.ring_ptr[ring + 1];
@@ -1642,7 +1654,7 @@ __global__ void __launch_bounds__(128, TWR_MINB) k_tile_round_w(PlanDev P, Works
 // The finish phase is serial work of one warp (a few thousand dependent instructions); as a kernel of its own it runs at
 // ~24 warps per SM instead of idling three of four warps of the producer CTA.
 // Meshes the lists cannot answer are queued in ws.fb_list2 for k_tile_round_w<true>.
-#define ZR_ROWS 56
+#define ZR_ROWS TBK_RTAB_ROWS
 struct ZoneRoundSmem {
 	double d[TBK_NPIX_TILE];          // staged residuals, NaN = masked
 	double rows[ZR_ROWS][TBK_RROW];   // the Taylor pieces this mesh can see (RadialTab rows jlo .. jlo + ZR_ROWS - 1), padded
@@ -1665,13 +1677,13 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 	const RadialTab rt = radial_tab(ws.rtab + (size_t)b * TBK_RSUB * max(P.nrings - 1, 1) * 8, c, P);
 	const int tile = P.nonflat_tiles[slot];
 	const int ty = tile / P.nx, tx = tile % P.nx;
-	// The static radius tile of the mesh (32 KB, contiguous) comes in through the TMA engine (one cp.async.bulk into sm.d,
-	// the residuals later overwrite it in place); meanwhile every thread has all of its pixel / mask loads in flight at once
-	// and the Taylor pieces between the smallest and largest radius of the mesh are staged (a mesh spans < 91 px).
+	// The static Taylor-piece words of the mesh (PlanDev::nonflat_uj, 32 KB, contiguous) come in through the TMA engine (one
+	// cp.async.bulk into sm.d, the residuals later overwrite them in place); meanwhile every thread has all of its pixel /
+	// mask loads in flight at once and the Taylor pieces the mesh can see are staged (a mesh spans < 91 px).
 	if (tid == 0) {
 		tma_bar_init(&sm.bar, 1);
 		tma_bar_expect(&sm.bar, (unsigned)(TBK_NPIX_TILE * sizeof(double)));
-		tma_load_1d(sm.d, P.nonflat_r + (size_t)slot * TBK_NPIX_TILE, (unsigned)(TBK_NPIX_TILE * sizeof(double)), &sm.bar);
+		tma_load_1d(sm.d, P.nonflat_uj + (size_t)slot * TBK_NPIX_TILE, (unsigned)(TBK_NPIX_TILE * sizeof(double)), &sm.bar);
 	}
 	// thread t, step i (0..7) owns row 8i + 2(t/32) + (t%32)/16, columns 4(t%16) .. +3
 	const int lrow0 = 2 * w + (lane >> 4), lcol = (lane & 15) << 2;
@@ -1685,37 +1697,49 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 			mks[i] = __ldg(reinterpret_cast<const unsigned int*>(mask + off0 + i * step));
 		}
 	}
-	int jlo = 0;
+	const int jlo = __ldg(P.nonflat_jlo + slot);
 	if (rt.radial_ok) {
-		const double2 rr = __ldg(P.nonflat_rr + slot);
-		jlo = max(0, min(rt.nsub - 1, (int)((clamp_d(rr.x, rt.x0, rt.xlast) - rt.center0) * rt.inv_h)) - 1);
-		const int jhi = min(rt.nsub - 1, max(0, min(rt.nsub - 1, (int)((clamp_d(rr.y, rt.x0, rt.xlast) - rt.center0) * rt.inv_h))) + 1);
-		if (jhi - jlo + 1 > ZR_ROWS) {   // cannot happen for meshes of 64 px and step / 8 >= 1.75 px; other parameters: bucketed path
+		if (jlo < 0) {   // cannot happen for meshes of 64 px and step / 8 >= 1.75 px; other parameters: bucketed path
 			__syncthreads();
 			if (tid == 0) { tma_bar_wait(&sm.bar, 0u); rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
 			return;
 		}
-		for (int e = tid; e < (jhi - jlo + 1) * 4; e += 128)
+		const int nrow = min(TBK_RTAB_ROWS, rt.nsub - jlo);
+		for (int e = tid; e < nrow * 4; e += 128)
 			reinterpret_cast<double2*>(&sm.rows[e >> 2][0])[e & 3] = __ldg(reinterpret_cast<const double2*>(rt.rows + 8 * (size_t)jlo) + e);
 	}
+	// the profile at the two ends of the spline (ext=3 clamp) and the pieces between them
+	double cflat = 0.0, clast = 0.0;
+	int j0 = 0, j1 = 0;
+	if (rt.radial_ok) { cflat = radial_tab_eval(rt, rt.x0); clast = radial_tab_eval(rt, rt.xlast); j0 = radial_tab_j0(rt); j1 = radial_tab_j1(rt); }
 	__syncthreads();                 // rows staged, barrier initialised
-	tma_bar_wait(&sm.bar, 0u);       // radius tile landed
+	tma_bar_wait(&sm.bar, 0u);       // piece words landed
 	{
-		const double cflat = rt.radial_ok ? radial_tab_eval_s(rt, &sm.rows[0][0], jlo, rt.x0) : 0.0;   // radial(r) for r <= x0 (ext=3 clamp)
 		int n = 0;
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			double2* cell = reinterpret_cast<double2*>(&sm.d[(lrow0 + 8 * i) * TBK_TILE + lcol]);
 			const double2 r01 = cell[0], r23 = cell[1];
 			const float x4[4] = {xs[i].x, xs[i].y, xs[i].z, xs[i].w};
-			const double rr[4] = {r01.x, r01.y, r23.x, r23.y};
+			const double uj[4] = {r01.x, r01.y, r23.x, r23.y};
 			double dd[4];
-			// inside r <= x0 the profile is the constant cflat: the whole warp skips the evaluation there
-			const bool beyond = rt.radial_ok && __any_sync(0xffffffffu, rr[3] > rt.x0 || rr[0] > rt.x0);
+			// where every pixel of the warp's two rows is clamped to the same end the evaluation is skipped
+			bool inner = false;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int jl = (int)((unsigned long long)__double_as_longlong(uj[q]) & 63ull);
+				inner |= jl < 62 && jlo + jl >= j0 && jlo + jl < j1;
+			}
+			const bool beyond = rt.radial_ok && __any_sync(0xffffffffu, inner);
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
 				const bool ok = !((mks[i] >> (8 * q)) & 0xFFu);
-				const double rad = beyond ? radial_tab_eval_s(rt, &sm.rows[0][0], jlo, rr[q]) : cflat;
+				double rad = 0.0;
+				if (beyond) rad = radial_tab_eval_uj(&sm.rows[0][0], jlo, j0, j1, cflat, clast, uj[q]);
+				else if (rt.radial_ok) {
+					const int jl = (int)((unsigned long long)__double_as_longlong(uj[q]) & 63ull);
+					rad = (jl == 62 || jlo + jl < j0) ? cflat : clast;
+				}
 				dd[q] = ok ? (double)x4[q] - rad : nan_d();
 				n += ok;
 			}
@@ -1791,7 +1815,7 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 	ZonePlan zp;
 	zp.ok = true; zp.mhat = sm.mhat; zp.shat = sm.shat; zp.pivot = pivot; zp.A = A; zp.B = Bv;
 	double ZL, ZH;
-	zone_range(zp, n, nA, nB, nM, nC, ZL, ZH);
+	zone_range(zp, n, nA, nB, nM, nC, ZL, ZH, false);
 	const bool tail_ovf = tq[0] > ZR_TQ || tq[1] > ZR_TQ || tq[2] > ZR_TQ || tq[3] > ZR_TQ;
 	if (!(ZL < ZH) || tail_ovf || n - nA - nB <= 0) {
 		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
@@ -2111,12 +2135,15 @@ struct FinalSmem {
 	double blk[5][TBK_FINAL_NM + 4];      // coefficient rows ty-2..ty+2, columns tx0-2..tx0+NM+1
 	double wT[4][64];                     // zoom weights transposed: wT[tap][phase] (conflict-free per-lane loads)
 	double R[TBK_FINAL_NM][2][64][4];     // row part for the left (coefficient columns 0..3) / right (1..4) mesh half
+	double rows[TBK_FINAL_NM][TBK_RTAB_ROWS][TBK_RROW];   // Taylor pieces of the radial profile seen by the non-flat meshes
 	int need_clip[TBK_FINAL_NM];
 };
 
-template <bool CLIP, bool NONFLAT>
+// RADIAL: 0 = constant radial term (flat mesh), 1 = Taylor-piece table (static piece words, PlanDev::nonflat_uj),
+// 2 = spline evaluation from the radius (meshes that see more pieces than the staged table holds: non-default parameters)
+template <bool CLIP, int RADIAL>
 __device__ __forceinline__ void final_rows(const FinalSmem& z, int m, const RadialSmem2& rs, const PlanDev& P,
-	double lo, double hi, double cflat, float* __restrict__ bkg, size_t img, int ty, int tx, int tid)
+	double lo, double hi, double cflat, double ctab0, double ctab1, int j0, int j1, float* __restrict__ bkg, size_t img, int ty, int tx, int tid)
 {
 	const int lcol = tile_lcol(tid), ox = lcol >> 5;
 	const int gx = tx * TBK_TILE + lcol;
@@ -2127,6 +2154,8 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, int m, const Radi
 		const double2 u1 = *reinterpret_cast<const double2*>(&z.wT[b][lcol + 2]);
 		wx[0][b] = u0.x; wx[1][b] = u0.y; wx[2][b] = u1.x; wx[3][b] = u1.y;
 	}
+	const int slot = RADIAL ? P.tile_slot[ty * P.nx + tx] : 0;
+	const int jlo = RADIAL == 1 ? __ldg(P.nonflat_jlo + slot) : 0;
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		const int lrow = tile_lrow(tid, j);
@@ -2136,8 +2165,8 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, int m, const Radi
 		const double r[4] = {ra.x, ra.y, rb.x, rb.y};
 		float o[4];
 		double rr[4] = {0.0, 0.0, 0.0, 0.0};
-		if (NONFLAT) {
-			const double* rp = P.nonflat_r + (size_t)P.tile_slot[ty * P.nx + tx] * TBK_NPIX_TILE + lrow * TBK_TILE + lcol;
+		if (RADIAL) {
+			const double* rp = (RADIAL == 1 ? P.nonflat_uj : P.nonflat_r) + (size_t)slot * TBK_NPIX_TILE + lrow * TBK_TILE + lcol;
 			const double2 r01 = __ldg(reinterpret_cast<const double2*>(rp)), r23 = __ldg(reinterpret_cast<const double2*>(rp + 2));
 			rr[0] = r01.x; rr[1] = r01.y; rr[2] = r23.x; rr[3] = r23.y;
 		}
@@ -2145,14 +2174,17 @@ __device__ __forceinline__ void final_rows(const FinalSmem& z, int m, const Radi
 		for (int q = 0; q < 4; ++q) {
 			double sq = wx[q][0] * r[0] + wx[q][1] * r[1] + wx[q][2] * r[2] + wx[q][3] * r[3];
 			if (CLIP) sq = clamp_d(sq, lo, hi);
-			const double rad = NONFLAT ? radial_value_s(rs, rr[q]) : cflat;
+			double rad = cflat;
+			if (RADIAL == 1) rad = radial_tab_eval_uj(&z.rows[m][0][0], jlo, j0, j1, ctab0, ctab1, rr[q]);
+			if (RADIAL == 2) rad = radial_value_s(rs, rr[q]);
 			o[q] = (float)(rad + sq);
 		}
 		*reinterpret_cast<float4*>(bkg + img + (size_t)gy * P.W + gx) = make_float4(o[0], o[1], o[2], o[3]);
 	}
 }
 
-__global__ void __launch_bounds__(TBK_NT, 4) k_final(PlanDev P, Workspace ws,
+template <int MINB>
+__global__ void __launch_bounds__(TBK_NT, MINB) k_final(PlanDev P, Workspace ws,
 	float* __restrict__ bkg, uint8_t* __restrict__ mask_out)
 {
 	__shared__ __align__(16) FinalSmem z;
@@ -2184,9 +2216,34 @@ __global__ void __launch_bounds__(TBK_NT, 4) k_final(PlanDev P, Workspace ws,
 	}
 	z.wT[tid & 3][tid >> 2] = __ldg(P.zoom_w + tid);
 	const bool radial = P.use_radial && c.radial_ok;
-	bool any_nonflat = false;
-	if (radial) for (int m = 0; m < nm; ++m) any_nonflat |= P.tile_slot[ty * P.nx + tx0 + m] >= 0;
-	if (any_nonflat) radial_stage(rs, c, P);
+	// radial term of the strip's meshes: 0 flat, 1 table, 2 spline
+	int rmode[TBK_FINAL_NM];
+	bool any_spline = false, any_tab = false;
+#pragma unroll
+	for (int m = 0; m < TBK_FINAL_NM; ++m) {
+		rmode[m] = 0;
+		if (radial && m < nm) {
+			const int slot = P.tile_slot[ty * P.nx + tx0 + m];
+			if (slot >= 0) rmode[m] = __ldg(P.nonflat_jlo + slot) >= 0 ? 1 : 2;
+		}
+		any_spline |= rmode[m] == 2; any_tab |= rmode[m] == 1;
+	}
+	if (any_spline) radial_stage(rs, c, P);
+	double ctab0 = 0.0, ctab1 = 0.0;
+	int j0 = 0, j1 = 0;
+	if (any_tab) {
+		const RadialTab rt = radial_tab(ws.rtab + (size_t)b * TBK_RSUB * max(P.nrings - 1, 1) * 8, c, P);
+		ctab0 = radial_tab_eval(rt, rt.x0); ctab1 = radial_tab_eval(rt, rt.xlast);
+		j0 = radial_tab_j0(rt); j1 = radial_tab_j1(rt);
+#pragma unroll
+		for (int m = 0; m < TBK_FINAL_NM; ++m) {
+			if (rmode[m] != 1) continue;
+			const int jlo = __ldg(P.nonflat_jlo + P.tile_slot[ty * P.nx + tx0 + m]);
+			const int nrow = min(TBK_RTAB_ROWS, rt.nsub - jlo);
+			for (int e = tid; e < nrow * 4; e += TBK_NT)
+				reinterpret_cast<double2*>(&z.rows[m][e >> 2][0])[e & 3] = __ldg(reinterpret_cast<const double2*>(rt.rows + 8 * (size_t)jlo) + e);
+		}
+	}
 	const double mesh_min = c.mesh_min, mesh_max = c.mesh_max;
 	const int mesh_const = c.mesh_const;
 	const double cflat = c.radial_ok ? c.c_flat : 0.0;
@@ -2213,16 +2270,21 @@ __global__ void __launch_bounds__(TBK_NT, 4) k_final(PlanDev P, Workspace ws,
 		if (B > 0) z.R[m][1][row][B - 1] = r;
 	}
 	__syncthreads();
-	for (int m = 0; m < nm; ++m) {
+#pragma unroll
+	for (int m = 0; m < TBK_FINAL_NM; ++m) {
+		if (m >= nm) break;
 		const int tx = tx0 + m;
-		const bool nonflat = radial && P.tile_slot[ty * P.nx + tx] >= 0;
+#define FINAL_ROWS(CL, RM) final_rows<CL, RM>(z, m, rs, P, mesh_min, mesh_max, cflat, ctab0, ctab1, j0, j1, bkg, img, ty, tx, tid)
 		if (z.need_clip[m]) {
-			if (nonflat) final_rows<true, true>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
-			else final_rows<true, false>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
+			if (rmode[m] == 1) FINAL_ROWS(true, 1);
+			else if (rmode[m] == 2) FINAL_ROWS(true, 2);
+			else FINAL_ROWS(true, 0);
 		} else {
-			if (nonflat) final_rows<false, true>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
-			else final_rows<false, false>(z, m, rs, P, mesh_min, mesh_max, cflat, bkg, img, ty, tx, tid);
+			if (rmode[m] == 1) FINAL_ROWS(false, 1);
+			else if (rmode[m] == 2) FINAL_ROWS(false, 2);
+			else FINAL_ROWS(false, 0);
 		}
+#undef FINAL_ROWS
 	}
 }
 
@@ -2301,7 +2363,7 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 			}
 			if (tile_kernel == 0) LAUNCH(TBK_K_RING_GATHER, (k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round)));
 			else LAUNCH(TBK_K_RING_GATHER, (k_ring_gather_t<<<dim3(P.n_ringtiles, B), 256, 0, st>>>(P, ws, cube, mask, round)));
-			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(P.nrings, B), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
+			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(B, P.nrings), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
 			LAUNCH(TBK_K_RADIAL_FIT, (k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B)));
 			if (P.n_nonflat > 0) {
 				if (tile_kernel == 0) LAUNCH(TBK_K_TILE_ROUND, (k_tile_round<<<dim3(P.n_nonflat, B), TBK_NT, 0, st>>>(P, ws, cube, mask)));
@@ -2321,7 +2383,12 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 		LAUNCH(TBK_K_MESH, (k_mesh_finalize<<<B, 1024, mesh_smem, st>>>(P, ws, status, round)));
 		if (!launch_ok("round")) return TBK_ERR_CUDA;
 	}
-	LAUNCH(TBK_K_FINAL, (k_final<<<dim3(P.ny * ((P.nx + TBK_FINAL_NM - 1) / TBK_FINAL_NM), B), TBK_NT, 0, st>>>(P, ws, bkg, mask)));
+	{
+		static const int final_minb = getenv("TBK_FINAL_MINB") ? atoi(getenv("TBK_FINAL_MINB")) : 3;
+		const dim3 gf(P.ny * ((P.nx + TBK_FINAL_NM - 1) / TBK_FINAL_NM), B);
+		if (final_minb != 4) LAUNCH(TBK_K_FINAL, (k_final<3><<<gf, TBK_NT, 0, st>>>(P, ws, bkg, mask)));
+		else LAUNCH(TBK_K_FINAL, (k_final<4><<<gf, TBK_NT, 0, st>>>(P, ws, bkg, mask)));
+	}
 	if (!launch_ok("final")) return TBK_ERR_CUDA;
 	if (prof) {
 		cudaError_t e = cudaStreamSynchronize(st);

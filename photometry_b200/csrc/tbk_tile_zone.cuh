@@ -98,7 +98,7 @@ __device__ __forceinline__ ZonePlan zone_plan(typename T::K sa, typename T::K sb
 // nC inside m -+ ZN_CW s.  nM says how many ranks the needed interval lies from m, nC gives the local density that turns
 // ranks into a value offset; the margins cover the Poisson noise of that conversion and the curvature of the density.
 #define ZN_CW 0.25
-__device__ __forceinline__ void zone_range(const ZonePlan& zp, int n, int nA, int nB, int nM, int nC, double& ZL, double& ZH)
+__device__ __forceinline__ void zone_range(const ZonePlan& zp, int n, int nA, int nB, int nM, int nC, double& ZL, double& ZH, bool nc_sampled)
 {
 	const int nbulk = n - nA - nB;
 	const double r_lo = (double)((n - 1 - nB) >> 1), r_hi = (double)(((n - 1 + nA) >> 1) + 1);
@@ -106,7 +106,8 @@ __device__ __forceinline__ void zone_range(const ZonePlan& zp, int n, int nA, in
 	// elements per unit value near the centre: counted, or (sparse centre) a Gaussian of the sample width
 	const double rho = local ? (double)nC / (2.0 * ZN_CW * zp.shat) : (double)max(nbulk, 1) * 0.418 / zp.shat;
 	const double dlo = r_lo - (double)nM, dhi = r_hi - (double)nM;
-	const double m0 = local ? 16.0 : 24.0, m1 = local ? 0.10 : 0.35;
+	// relative margin: 0.10 covers the curvature of the density; an nC extrapolated from a quarter of the elements carries +-7 % (1 sigma) more
+	const double m0 = local ? 16.0 : 24.0, m1 = local ? (nc_sampled ? 0.15 : 0.10) : 0.35;
 	const double mlo = m0 + m1 * fabs(dlo), mhi = m0 + m1 * fabs(dhi);
 	ZL = fmax(zp.mhat + (dlo - mlo) / rho, zp.A);
 	ZH = fmin(zp.mhat + (dhi + mhi) / rho, zp.B);
@@ -133,14 +134,29 @@ __device__ __forceinline__ uint32_t zone_scan_bins(uint32_t* cnt, int lane, uint
 	return start0;
 }
 
-// The keys are grouped by bin; every lane insertion-sorts the keys of its own 4 consecutive bins (a handful), after which
-// zone[] is sorted as a whole and the key of a rank is a single load.
+// The keys are grouped by bin; every lane sorts the keys of its own 4 consecutive bins (a handful): the first 8 through a
+// 19-comparator network in registers, any further ones by insertion into that sorted run.  Afterwards zone[] is sorted
+// as a whole and the key of a rank is a single load.
 template <typename K>
-__device__ __forceinline__ bool zone_sort_bins(K* zone, uint32_t s, uint32_t e)
+__device__ __forceinline__ bool zone_sort_bins(K* zone, uint32_t s, uint32_t e, K pad)
 {
-	const bool ok = e - s <= (uint32_t)ZN_LANEMAX;
-	if (ok) {
-		for (uint32_t i = s + 1; i < e; ++i) {
+	const uint32_t m = e - s;
+	const bool ok = m <= (uint32_t)ZN_LANEMAX;
+	if (m > 1u && ok) {
+		K a[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) a[i] = (uint32_t)i < m ? zone[s + i] : pad;
+#define ZN_CX(i, j) { const K lo_ = min(a[i], a[j]), hi_ = max(a[i], a[j]); a[i] = lo_; a[j] = hi_; }
+		ZN_CX(0, 1) ZN_CX(2, 3) ZN_CX(4, 5) ZN_CX(6, 7)
+		ZN_CX(0, 2) ZN_CX(1, 3) ZN_CX(4, 6) ZN_CX(5, 7)
+		ZN_CX(1, 2) ZN_CX(5, 6)
+		ZN_CX(0, 4) ZN_CX(1, 5) ZN_CX(2, 6) ZN_CX(3, 7)
+		ZN_CX(2, 4) ZN_CX(3, 5)
+		ZN_CX(1, 2) ZN_CX(3, 4) ZN_CX(5, 6)
+#undef ZN_CX
+#pragma unroll
+		for (int i = 0; i < 8; ++i) if ((uint32_t)i < m) zone[s + i] = a[i];
+		for (uint32_t i = s + 8u; i < e; ++i) {
 			const K v = zone[i];
 			uint32_t p = i;
 			while (p > s && zone[p - 1] > v) { zone[p] = zone[p - 1]; --p; }
@@ -307,7 +323,7 @@ __device__ bool zone_finish(ZoneSmem<T>& sm, int lane, int n, int nA, int nB, in
 			}
 		}
 		__syncwarp();
-		if (!zone_sort_bins(sm.zone, start0, bend[ZN_BINS / 32 - 1])) return false;
+		if (!zone_sort_bins(sm.zone, start0, bend[ZN_BINS / 32 - 1], T::padkey())) return false;
 		__syncwarp();
 	}
 	const Raw* tl = sm.tails;
@@ -345,7 +361,7 @@ __device__ bool zone_finish_seg(const typename T::Raw* gt, int tcap, const int (
 	__syncwarp();
 	zone_each([&](Raw r) { zone[atomicAdd(&cnt[min(ZN_BINS - 1, (int)(T::offs(r, zl) * zscale))], 1u)] = T::key_of(r); });
 	__syncwarp();
-	if (!zone_sort_bins(zone, start0, bend[ZN_BINS / 32 - 1])) return false;
+	if (!zone_sort_bins(zone, start0, bend[ZN_BINS / 32 - 1], T::padkey())) return false;
 	__syncwarp();
 	// tail element i of the dense order "segment 0, segment 1, ..."
 	auto tail_at = [&](int i) -> Raw {
