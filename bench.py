@@ -357,10 +357,10 @@ def run_b200(args):
 		b = min(a + chunk, n)
 		fit.fit(cube[a:b], meta_d[a * isz:b * isz], bkg_out=bkg[a:b], mask_out=mask[a:b], profile=prof)
 	ncalls = (n + chunk - 1) // chunk
-	dom = max((k for k in prof if k != 'misc'), key=lambda k: prof[k])
-	# launches per tbk_fit_batch and class (3 rounds): zone statistics + queued bucketed fallback for the raw pixels; per round
-	# producer + finish + queued fallback for the residuals
-	launches_per_call = {'tile_base': 2, 'tile_round': 9, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
+	dom = max((k for k in prof if k not in ('misc', 'fallback')), key=lambda k: prof[k])
+	# launches per tbk_fit_batch and class (3 rounds): zone statistics of the raw pixels; per round producer + finish for the
+	# residuals; 'fallback' = the bucketed kernels for the queued meshes (1 + 3; on a side stream outside the profiled call)
+	launches_per_call = {'tile_base': 1, 'tile_round': 6, 'fallback': 4, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
 	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
 	peak, peak_src = load_peaks()
 	# The fit is a chain of ~32 kernel launches per batch and no single kernel dominates (the largest is < 30 % of

@@ -151,6 +151,7 @@ enum {
 	TBK_K_RADIAL_FIT,      /* moving median + spline */
 	TBK_K_MESH,            /* mesh estimator, IDW, 3x3 median, prefilter */
 	TBK_K_FINAL,           /* mesh-to-pixel interpolation + radial + write */
+	TBK_K_FALLBACK,        /* bucketed statistics of the meshes the zone kernels queued (a side stream outside the profiled call) */
 	TBK_K_MISC,            /* per-FFI bookkeeping kernels */
 	TBK_K_COUNT
 };

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get('TBK_LIBPATH') or os.path.join(_HERE, 'lib', 'libtbk.so')   # override: development builds only
 
 TBK_MAX_ROUNDS = 8
-KERNEL_CLASSES = ('tile_base', 'tile_round', 'zp_min', 'ring_gather', 'ring_kde', 'radial_fit', 'mesh', 'final', 'misc')
+KERNEL_CLASSES = ('tile_base', 'tile_round', 'zp_min', 'ring_gather', 'ring_kde', 'radial_fit', 'mesh', 'final', 'fallback', 'misc')
 
 
 class TbkError(RuntimeError):
