@@ -329,14 +329,22 @@ struct ZbStage {
 	float px[ZB_WARPS][TBK_NPIX_TILE];
 	unsigned long long bar[ZB_WARPS];
 };
-template <bool HAS_EXTRA, bool STAGED>
+// RETRY = true: the launch works off the retry queue (ws.fb_list2 during the raw-pixel phase, count in fb_count[8]); a
+// warp takes queue entry blockIdx.x * ZB_WARPS + w, the plan comes from the statistics parked in the mesh's TileStat.
+template <bool HAS_EXTRA, bool STAGED, bool RETRY>
 __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out)
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out, int B)
 {
 	__shared__ ZoneSmem<Zn32> smw[ZB_WARPS];
 	extern __shared__ __align__(128) unsigned char zb_dyn[];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int tile = blockIdx.x * ZB_WARPS + w, b = blockIdx.y;
+	int tile = blockIdx.x * ZB_WARPS + w, b = blockIdx.y;
+	if (RETRY) {
+		const int e = blockIdx.x * ZB_WARPS + w;
+		if (e >= min(ws.fb_count[8], B * P.n_nonflat)) return;
+		const int ent = ws.fb_list2[e];
+		b = ent / P.ntiles; tile = ent % P.ntiles;
+	}
 	if (tile >= P.ntiles) return;
 	ZoneSmem<Zn32>& sm = smw[w];
 	const int ty = tile / P.nx, tx = tile % P.nx;
@@ -384,7 +392,11 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 	// ---- sample: 2 x 32 pixels spread over the mesh
 	ZonePlan zp;
 	zp.ok = false; zp.mhat = 0.0; zp.shat = 1.0; zp.pivot = 0.0; zp.A = 0.0; zp.B = 0.0;
-	if (do_stats) {
+	if (RETRY) {
+		const TileStat pv = ws.tile_base[(size_t)b * P.ntiles + tile];
+		zp.ok = pv.std > 0.0; zp.mhat = pv.med; zp.shat = 0.75 * pv.std; zp.pivot = Zn32::pivot_of(zp.mhat);
+		zp.A = zp.mhat - ZN_CT * zp.shat; zp.B = zp.mhat + ZN_CT * zp.shat;   // median -+ 1.5 sigma of the failing iteration: half its clip range
+	} else if (do_stats) {
 		uint32_t sk[2];
 #pragma unroll
 		for (int t = 0; t < 2; ++t) {
@@ -398,6 +410,10 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 		}
 		zp = zone_plan<Zn32>(sk[0], sk[1], lane);
 	}
+	TileStat st;
+	TileStat* dst = ws.tile_base + (size_t)b * P.ntiles + tile;
+	bool good = false;
+	int why = ZN_WHY_SAMPLE;
 	// bulk = [kA, kB] as keys; kM: keys below the sample centre.  Without a usable sample: empty bulk, every valid
 	// pixel is a "tail" (the lists overflow harmlessly and the mesh goes to the bucketed path).
 	uint32_t kA = 1u, kB = 0u, kM = 0u;
@@ -473,15 +489,14 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 	kmin = __reduce_min_sync(0xffffffffu, kmin);
 	const int n = 4096 - __reduce_add_sync(0xffffffffu, nbad);
 	nz = __reduce_or_sync(0xffffffffu, nz);
-	if (lane == 0) {
+	if (lane == 0 && !RETRY) {
 		if (nz && !c.any_nonzero) atomicOr(&c.any_nonzero, 1);
 		if (n > 0) { atomicAdd(&c.n_valid, n); atomicMin(&c.min_bits, kmin); }
 	}
-	TileStat st;
 	st.mean = st.med = st.std = nan_d(); st.nfin = 0; st.pad = 0;
-	TileStat* dst = ws.tile_base + (size_t)b * P.ntiles + tile;
 	if (!do_stats || n == 0) { if (lane == 0) *dst = st; return; }
-	bool good = zp.ok && n >= ZN_MIN_N;
+	good = zp.ok && n >= ZN_MIN_N;
+	why = ZN_WHY_SAMPLE;
 	if (good) {
 		const int tcnt = (int)((tptr - tbase) >> 7);
 		const int nT = __reduce_add_sync(0xffffffffu, tcnt);
@@ -494,6 +509,7 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 		good = Zn32::key_floor(ZH, kZH);
 		kZH = min(kZH, kB);
 		good = good && kZL <= kZH;
+		why = ZN_WHY_RANGE;
 		if (good) {
 			// ---- pass 2 (L2): zone elements into the per-lane lists; elements below the zone are counted
 			const uint32_t zspan = kZH - kZL;
@@ -532,12 +548,22 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 			const float zscale = (float)ZN_BINS / ((float)zspan + 1.0f);
 			__syncwarp();
 			good = zone_finish<Zn32>(sm, lane, n, nA, nB, nZL, tcnt, zcnt, s1, s2, pivot,
-				(double)__uint_as_float(kA), (double)__uint_as_float(kB), kZL, zscale, st);
+				(double)__uint_as_float(kA), (double)__uint_as_float(kB), kZL, zscale, st, why);
 		}
 	}
 	if (lane == 0) {
 		if (good) *dst = st;
-		else ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile;
+		else {
+			// A clip bound that entered the bulk (the 64-pixel sample overestimated the width: star wings, gradients) does not
+			// send the mesh to the bucketed path straight away: the statistics of the failing iteration are exact, so the mesh
+			// is queued for ONE more run of this kernel (RETRY) with the bulk placed around them; they travel in *dst.
+			bool retry = false;
+			if (!RETRY && why == ZN_WHY_BOUND && st.std > 0.0) {
+				const int pos = atomicAdd(ws.fb_count + 8, 1);
+				if (pos < B * P.n_nonflat) { *dst = st; ws.fb_list2[pos] = b * P.ntiles + tile; retry = true; }
+			}
+			if (!retry) { ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile; atomicAdd(ws.fb_count + 16 + why, 1); }
+		}
 	}
 }
 
@@ -1701,7 +1727,7 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 	if (rt.radial_ok) {
 		if (jlo < 0) {   // cannot happen for meshes of 64 px and step / 8 >= 1.75 px; other parameters: bucketed path
 			__syncthreads();
-			if (tid == 0) { tma_bar_wait(&sm.bar, 0u); rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
+			if (tid == 0) { tma_bar_wait(&sm.bar, 0u); rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; atomicAdd(ws.fb_count + 24 + ZN_WHY_EMPTY, 1); }
 			return;
 		}
 		const int nrow = min(TBK_RTAB_ROWS, rt.nsub - jlo);
@@ -1757,7 +1783,16 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 			const double v = sm.d[(lane * 131 + 17 + t * 2053) & (TBK_NPIX_TILE - 1)];
 			sk[t] = (v == v) ? dkey(v) : Zn64::padkey();
 		}
-		const ZonePlan zp = zone_plan<Zn64>(sk[0], sk[1], lane);
+		ZonePlan zp = zone_plan<Zn64>(sk[0], sk[1], lane);
+		if (round > 0 && zp.ok) {
+			// the width of the previous round's clipped distribution of this mesh is a far better scale than the IQR of 64
+			// samples (star wings inflate it, and a bulk wider than the final clip range costs a fallback); the centre stays
+			// the fresh sample's, because the radial profile moves between rounds
+			const TileStat prev = ws.tile_nf[(size_t)b * P.n_nonflat + slot];
+			if (prev.nfin >= ZN_MIN_N && prev.std > 0.0 && prev.std < zp.shat) {
+				zp.shat = prev.std; zp.A = zp.mhat - ZN_CT * zp.shat; zp.B = zp.mhat + ZN_CT * zp.shat;
+			}
+		}
 		if (lane == 0) {
 			sm.ok = zp.ok; sm.A = zp.A; sm.B = zp.B; sm.M = zp.mhat; sm.mhat = zp.mhat; sm.shat = zp.shat; sm.pivot = zp.pivot;
 			sm.n = sm.redi[0][0] + sm.redi[1][0] + sm.redi[2][0] + sm.redi[3][0];
@@ -1774,7 +1809,7 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 		return;
 	}
 	if (!sm.ok || n < ZN_MIN_N) {
-		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
+		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; atomicAdd(ws.fb_count + 24 + ZN_WHY_SAMPLE, 1); }
 		return;
 	}
 	const double A = sm.A, Bv = sm.B, M = sm.M, pivot = sm.pivot;
@@ -1818,7 +1853,7 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 	zone_range(zp, n, nA, nB, nM, nC, ZL, ZH, false);
 	const bool tail_ovf = tq[0] > ZR_TQ || tq[1] > ZR_TQ || tq[2] > ZR_TQ || tq[3] > ZR_TQ;
 	if (!(ZL < ZH) || tail_ovf || n - nA - nB <= 0) {
-		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; }
+		if (tid == 0) { rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; atomicAdd(ws.fb_count + 24 + ZN_WHY_RANGE, 1); }
 		return;
 	}
 	__syncthreads();   // redi is reused below
@@ -1843,7 +1878,7 @@ __global__ void __launch_bounds__(128, 5) k_tile_round_z(PlanDev P, Workspace ws
 	if (tid != 0) return;
 	const int zq[4] = {sm.redi[0][1], sm.redi[1][1], sm.redi[2][1], sm.redi[3][1]};
 	if (zq[0] > ZR_ZQ || zq[1] > ZR_ZQ || zq[2] > ZR_ZQ || zq[3] > ZR_ZQ || zq[0] + zq[1] + zq[2] + zq[3] == 0) {
-		rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot;
+		rec.state = 0; ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; atomicAdd(ws.fb_count + 24 + ZN_WHY_LIST, 1);
 		return;
 	}
 	rec.n = n; rec.nA = nA; rec.nB = nB; rec.nZL = sm.redi[0][0] + sm.redi[1][0] + sm.redi[2][0] + sm.redi[3][0];
@@ -1875,12 +1910,13 @@ __global__ void __launch_bounds__(32 * ZF_WARPS, 6) k_tile_round_fin(PlanDev P, 
 	const float zscale = (float)ZN_BINS / (float)(ZH - ZL) * 0.99999f;
 	TileStat st;
 	bool good = nZ <= ZF_ZCAP;
+	int why = ZN_WHY_LIST;
 	// the tails go from the four quarters (global memory, L2) straight into the registers of the clip sweeps
 	if (good) good = zone_finish_seg<Zn64, 4, 4>(gt, ZR_TQ, tq, gz, ZR_ZQ, zq, sm.zone, sm.cnt, lane,
-		rec.n, rec.nA, rec.nB, rec.nZL, rec.s1, rec.s2, rec.pivot, rec.A, rec.B, ZL, zscale, st);
+		rec.n, rec.nA, rec.nB, rec.nZL, rec.s1, rec.s2, rec.pivot, rec.A, rec.B, ZL, zscale, st, why);
 	if (lane == 0) {
 		if (good) ws.tile_nf[(size_t)b * P.n_nonflat + slot] = st;
-		else ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot;
+		else { ws.fb_list2[atomicAdd(ws.fb_count + 1 + round, 1)] = b * P.n_nonflat + slot; atomicAdd(ws.fb_count + 24 + why, 1); }
 	}
 }
 
@@ -2331,18 +2367,27 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 			// measured alternative: mesh staged in shared memory by TMA bulk copies
 			static bool attr_set = false;
 			if (!attr_set) {
-				cudaFuncSetAttribute(k_tile_base_z<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
-				cudaFuncSetAttribute(k_tile_base_z<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
+				cudaFuncSetAttribute(k_tile_base_z<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
+				cudaFuncSetAttribute(k_tile_base_z<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
 				attr_set = true;
 			}
-			if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, true><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask)));
-			else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, true><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask)));
+			if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, true, false><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask, B)));
+			else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, true, false><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask, B)));
 		}
-		else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
-		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask)));
+		else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask, B)));
+		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask, B)));
 		// the queued meshes (bucketed statistics) are only needed by k_mesh_finalize: side stream, joined before round 0's
 		cudaStream_t fs = st;
 		if (side && !prof) { fs = side->stream; cudaEventRecord(side->fork, st); cudaStreamWaitEvent(fs, side->fork, 0); base_forked = true; }
+		{
+			// second run of the zone kernel for the meshes whose first plan put a clip bound inside the bulk (queue capacity
+			// B * n_nonflat entries, one warp per entry; warps beyond the queue length leave at once)
+			const dim3 gr((B * P.n_nonflat + ZB_WARPS - 1) / ZB_WARPS, 1);
+			if (gr.x > 0) {
+				if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<true, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, B)));
+				else LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<false, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, B)));
+			}
+		}
 		if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<true><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
 		else LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<false><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
 		if (base_forked) cudaEventRecord(side->join, fs);

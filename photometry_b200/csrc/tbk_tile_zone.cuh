@@ -114,6 +114,14 @@ __device__ __forceinline__ void zone_range(const ZonePlan& zp, int n, int nA, in
 }
 
 // ---- pieces of the finish phase (one warp) ----------------------------------------------------------------------
+// why a mesh went to the bucketed path (diagnostic counters, Workspace::fb_count[16 + 8 * kind + why])
+#define ZN_WHY_SAMPLE 1    // unusable sample or fewer than ZN_MIN_N valid pixels
+#define ZN_WHY_RANGE 2     // empty zone range
+#define ZN_WHY_LIST 3      // tail / zone list overflow
+#define ZN_WHY_SORT 4      // a lane's zone bins too full
+#define ZN_WHY_RANK 5      // a median rank outside the zone
+#define ZN_WHY_BOUND 6     // a clip bound entered the bulk
+#define ZN_WHY_EMPTY 7     // empty bulk or zone
 #define ZN_TREG 12        // tail elements per lane held in registers across the clip iterations (more: re-read from memory)
 #define ZN_LANEMAX 64     // a lane never sorts more zone keys than this (4 bins); fuller bins send the mesh to the bucketed path
 
@@ -172,7 +180,7 @@ __device__ __forceinline__ bool zone_sort_bins(K* zone, uint32_t s, uint32_t e, 
 // bucketed path).
 template <typename T, typename TailAt>
 __device__ bool zone_iterate(TailAt tail_at, const typename T::K* zone, int lane,
-	int n, int nA, int nB, int nZL, int nZ, double s1b, double s2b, double pivot, double vA, double vB, TileStat& out)
+	int n, int nA, int nB, int nZL, int nZ, double s1b, double s2b, double pivot, double vA, double vB, TileStat& out, int& why)
 {
 	typedef typename T::K K;
 	typedef typename T::Raw Raw;
@@ -239,32 +247,34 @@ __device__ bool zone_iterate(TailAt tail_at, const typename T::K* zone, int lane
 		const double sd = sqrt(fmax((s2b + t2) / (double)ni - m1 * m1, 0.0));
 		const int q = below + ((ni - 1) >> 1) - nZL;
 		const bool two = (ni & 1) == 0;
-		if (q < 0 || q + (two ? 1 : 0) >= nZ) return false;
+		if (q < 0 || q + (two ? 1 : 0) >= nZ) { why = ZN_WHY_RANK; return false; }
 		const double med = zone_median(q, two);
 		if (fin) { out.nfin = ni; out.mean = pivot + m1; out.std = sd; out.med = med; return true; }
 		lo_last = med - 3.0 * sd; hi_last = med + 3.0 * sd;
 		nested_last = lo_last >= lo_run && hi_last <= hi_run;
 		lo_run = fmax(lo_run, lo_last); hi_run = fmin(hi_run, hi_last);
-		if (lo_run > vA || hi_run < vB) return false;   // a bound entered the bulk
+		if (lo_run > vA || hi_run < vB) {   // a bound entered the bulk: the statistics of this iteration are still exact, the caller may re-plan around them
+			why = ZN_WHY_BOUND; out.med = med; out.std = sd; out.nfin = ni; return false;
+		}
 		n_prev = ni; mean_c = pivot + m1; sd_c = sd; med_c = med;
 	}
-	return false;   // not reached
+	why = ZN_WHY_EMPTY; return false;   // not reached
 }
 
 // Finish from per-lane lists in shared memory (the fused raw-pixel kernel).  tcnt / zcnt: this lane's list lengths;
 // zl / zscale: zone bin map; the other arguments are warp-uniform.
 template <typename T>
 __device__ bool zone_finish(ZoneSmem<T>& sm, int lane, int n, int nA, int nB, int nZL, int tcnt, int zcnt,
-	double s1b, double s2b, double pivot, double vA, double vB, typename T::Raw zl, float zscale, TileStat& out)
+	double s1b, double s2b, double pivot, double vA, double vB, typename T::Raw zl, float zscale, TileStat& out, int& why)
 {
 	typedef typename T::Raw Raw;
 	out.mean = out.med = out.std = nan_d();
 	out.nfin = 0; out.pad = 0;
-	if (n - nA - nB <= 0) return false;
-	if (__any_sync(0xffffffffu, tcnt > ZN_TCAP || zcnt > ZN_ZCAP)) return false;
+	if (n - nA - nB <= 0) { why = ZN_WHY_EMPTY; return false; }
+	if (__any_sync(0xffffffffu, tcnt > ZN_TCAP || zcnt > ZN_ZCAP)) { why = ZN_WHY_LIST; return false; }
 	const int nT = nA + nB;
 	const int nZ = __reduce_add_sync(0xffffffffu, zcnt);
-	if (nZ == 0) return false;
+	if (nZ == 0) { why = ZN_WHY_EMPTY; return false; }
 	__syncwarp();
 	// ---- tails: per-lane lists -> dense, in place (row j is read completely before anything is written, and the
 	// dense positions of row j never lie beyond row j)
@@ -323,11 +333,11 @@ __device__ bool zone_finish(ZoneSmem<T>& sm, int lane, int n, int nA, int nB, in
 			}
 		}
 		__syncwarp();
-		if (!zone_sort_bins(sm.zone, start0, bend[ZN_BINS / 32 - 1], T::padkey())) return false;
+		if (!zone_sort_bins(sm.zone, start0, bend[ZN_BINS / 32 - 1], T::padkey())) { why = ZN_WHY_SORT; return false; }
 		__syncwarp();
 	}
 	const Raw* tl = sm.tails;
-	return zone_iterate<T>([&](int i) { return tl[i]; }, sm.zone, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out);
+	return zone_iterate<T>([&](int i) { return tl[i]; }, sm.zone, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out, why);
 }
 
 // Finish from lists that are not per-lane: tails in TSEG segments of capacity tcap with tq[s] entries, zone elements in
@@ -337,16 +347,16 @@ template <typename T, int TSEG, int ZSEG>
 __device__ bool zone_finish_seg(const typename T::Raw* gt, int tcap, const int (&tq)[TSEG],
 	const typename T::Raw* gz, int zcap, const int (&zq)[ZSEG], typename T::K* zone, uint32_t* cnt, int lane,
 	int n, int nA, int nB, int nZL, double s1b, double s2b, double pivot, double vA, double vB, typename T::Raw zl, float zscale,
-	TileStat& out)
+	TileStat& out, int& why)
 {
 	typedef typename T::Raw Raw;
 	out.mean = out.med = out.std = nan_d();
 	out.nfin = 0; out.pad = 0;
-	if (n - nA - nB <= 0) return false;
+	if (n - nA - nB <= 0) { why = ZN_WHY_EMPTY; return false; }
 	int nZ = 0;
 #pragma unroll
 	for (int s = 0; s < ZSEG; ++s) nZ += zq[s];
-	if (nZ == 0) return false;
+	if (nZ == 0) { why = ZN_WHY_EMPTY; return false; }
 	uint32_t bend[ZN_BINS / 32];
 #pragma unroll
 	for (int j = 0; j < ZN_BINS / 32; ++j) cnt[lane + 32 * j] = 0u;
@@ -361,7 +371,7 @@ __device__ bool zone_finish_seg(const typename T::Raw* gt, int tcap, const int (
 	__syncwarp();
 	zone_each([&](Raw r) { zone[atomicAdd(&cnt[min(ZN_BINS - 1, (int)(T::offs(r, zl) * zscale))], 1u)] = T::key_of(r); });
 	__syncwarp();
-	if (!zone_sort_bins(zone, start0, bend[ZN_BINS / 32 - 1], T::padkey())) return false;
+	if (!zone_sort_bins(zone, start0, bend[ZN_BINS / 32 - 1], T::padkey())) { why = ZN_WHY_SORT; return false; }
 	__syncwarp();
 	// tail element i of the dense order "segment 0, segment 1, ..."
 	auto tail_at = [&](int i) -> Raw {
@@ -370,5 +380,5 @@ __device__ bool zone_finish_seg(const typename T::Raw* gt, int tcap, const int (
 		for (int t = 0; t < TSEG - 1; ++t) { if (s == t && i >= tq[t]) { i -= tq[t]; s = t + 1; } }
 		return gt[s * tcap + i];
 	};
-	return zone_iterate<T>(tail_at, zone, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out);
+	return zone_iterate<T>(tail_at, zone, lane, n, nA, nB, nZL, nZ, s1b, s2b, pivot, vA, vB, out, why);
 }

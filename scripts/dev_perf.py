@@ -28,7 +28,7 @@ for chunk in [int(a) for a in sys.argv[1:]] or [16, 64]:
 	print(f"chunk={chunk}: {n / ms * 1e3:.0f} FFIs/s ({ms / n * 1e3:.1f} us/FFI)  per-FFI us: " + ' '.join(f"{k}={v / n * 1e3:.1f}" for k, v in prof.items()), flush=True)
 
 
-for ns, chunk in (() if NOSTACK else ((2, 32), (2, 64), (3, 32), (4, 16), (3, 64), (4, 64))):
+for ns, chunk in (() if NOSTACK else ((2, 64), (3, 64), (4, 64), (4, 96), (4, 128), (6, 64), (6, 32), (8, 32), (8, 64))):
 	for rep in range(2):
 		torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True); e0.record()
 		fit.fit_stack(cube, meta, bk, mk, chunk=chunk, nstreams=ns)

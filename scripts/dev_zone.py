@@ -13,3 +13,5 @@ for name, cam, ccd, kw in (('config 2', 1, 2, {}), ('crowded', 2, 3, dict(n_star
 	fit.fit(cube, pb.meta_from_headers(hdrs))
 	fb = fit.debug_workspace()['fallbacks']
 	print(f"{name}: {n} FFIs, fallback counters {fb[:5].tolist()} of {n * 1024} meshes ({100.0 * fb[0] / (n * 1024):.2f} % raw-pixel)", flush=True)
+	why = ('-', 'sample', 'range', 'list', 'sort', 'rank', 'bound', 'empty')
+	print("   raw-pixel reasons: " + ' '.join(f"{why[i]}={fb[16 + i]}" for i in range(1, 8)) + "   residual reasons (3 rounds): " + ' '.join(f"{why[i]}={fb[24 + i]}" for i in range(1, 8)), flush=True)
