@@ -69,6 +69,11 @@ typedef struct tbk_plan tbk_plan;
  *   camera, ccd     1..4 when is_tess (unknown pair -> TBK_ERR_INVALID, backgrounds.py:139-140)
  *   xycen_override  NULL, or {x, y} replacing the camera-centre table (test hook)
  *   other args      the keyword arguments of fit_background (backgrounds.py:52-53)
+ * Development switches, read from the environment when the plan is created (all variants give the same statistics and are
+ * cross-checked by tests/test_gpu_parity.py::test_kernel_variants_agree):
+ *   TBK_TILE_KERNEL = 6 (default) zone kernels, 0 CTA-per-mesh histogram kernels, 3 bucketed warp kernels,
+ *                     7 zone kernels with the raw mesh staged by TMA bulk copies (the measured alternative, slower)
+ *   TBK_FINAL_MINB  = 3 (default) | 4 resident CTAs per SM the final kernel is compiled for
  */
 int tbk_plan_create(tbk_plan** plan, int H, int W, int is_tess, int camera, int ccd,
 	double flux_cutoff, int bkgiters, double radial_cutoff, double radial_pixel_step,
