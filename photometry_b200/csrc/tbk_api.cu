@@ -189,6 +189,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	std::vector<double> nonflat_r;
 	std::vector<double2> nonflat_rr;
 	std::vector<double> nonflat_uj;
+	std::vector<int> ringtile_idx;
 	std::vector<int> nonflat_jlo;
 	if (P.use_radial) {
 		// backgrounds.py:145-154
@@ -250,6 +251,11 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 				ringtile_ent[fill2[slot_of[t]]++] = ((unsigned)j << 12) | (unsigned)(((y % TBK_TILE) << 6) | (x % TBK_TILE));
 			}
 			P.n_ringtiles = (int)ringtile_id.size();
+			// dense form of the same map for the gather kernel (87 % of the pixels of these meshes are ring pixels)
+			ringtile_idx.assign(ringtile_id.size() * (size_t)TBK_NPIX_TILE, -1);
+			for (size_t k = 0; k < ringtile_id.size(); ++k)
+				for (int e = ringtile_ptr[k]; e < ringtile_ptr[k + 1]; ++e)
+					ringtile_idx[k * TBK_NPIX_TILE + (ringtile_ent[e] & 4095u)] = (int)(ringtile_ent[e] >> 12);
 		}
 		// meshes that reach beyond the first ring centre see a non-constant radial component
 		const double c0 = host_edge(radial_cutoff, radial_pixel_step, 1) - radial_pixel_step / 2;
@@ -342,7 +348,7 @@ extern "C" int tbk_plan_create(tbk_plan** out, int H, int W, int is_tess, int ca
 	if ((rc = upload(p, ring_order, &P.ring_order)) || (rc = upload(p, ring_ptr, &P.ring_ptr)) || (rc = upload(p, ring_pix, &P.ring_pix)) ||
 		(rc = upload(p, nonflat, &P.nonflat_tiles)) || (rc = upload(p, tile_slot, &P.tile_slot)) ||
 		(rc = upload(p, zw, &P.zoom_w)) || (rc = upload(p, tw, &P.twiddle)) ||
-		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, nonflat_rr, &P.nonflat_rr)) || (rc = upload(p, nonflat_uj, &P.nonflat_uj)) || (rc = upload(p, nonflat_jlo, &P.nonflat_jlo)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent))) {
+		(rc = upload(p, nonflat_r, &P.nonflat_r)) || (rc = upload(p, nonflat_rr, &P.nonflat_rr)) || (rc = upload(p, nonflat_uj, &P.nonflat_uj)) || (rc = upload(p, nonflat_jlo, &P.nonflat_jlo)) || (rc = upload(p, ringtile_id, &P.ringtile_id)) || (rc = upload(p, ringtile_ptr, &P.ringtile_ptr)) || (rc = upload(p, ringtile_ent, &P.ringtile_ent)) || (rc = upload(p, ringtile_idx, &P.ringtile_idx))) {
 		tbk_plan_destroy(p);
 		return rc;
 	}

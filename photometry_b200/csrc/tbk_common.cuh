@@ -39,6 +39,7 @@ struct PlanDev {
 	const int* ringtile_id;     // [n_ringtiles] mesh id
 	const int* ringtile_ptr;    // [n_ringtiles + 1] CSR offsets into ringtile_ent
 	const unsigned* ringtile_ent; // [nringpix] (index into the ring-ordered sample array << 12) | (row << 6 | col) within the mesh
+	const int* ringtile_idx;    // [n_ringtiles][64*64] the same as a dense map: index into the ring-ordered sample array, -1 = no ring pixel
 	uint32_t* idw_cache;        // [1 + TBK_IDW_CACHE entries]: entries used, then {state, good-mesh bitmap, neighbour table} each
 	const double* zoom_w;       // [64][4] cubic B-spline weights per sub-tile phase
 	const double2* twiddle;     // [TBK_KDE_M/2] exp(-2 pi i k / M)

@@ -916,6 +916,92 @@ __global__ void __launch_bounds__(256) k_ring_gather_t(PlanDev P, Workspace ws, 
 	}
 }
 
+// K_ring_gather_d: the same samples from the dense per-mesh map (PlanDev::ringtile_idx).  Almost every pixel of a mesh
+// that touches the rings is a ring pixel, so the mesh is walked densely -- a thread owns one column and 16 rows, a warp
+// reads 32 consecutive indices / mask bytes / pixels per row, the four column weights stay in registers and the row
+// part of the zoom is one shared-memory broadcast per warp and row -- instead of through the entry list, whose loads
+// scatter over the mesh.
+__global__ void __launch_bounds__(256, 4) k_ring_gather_d(PlanDev P, Workspace ws, const float* __restrict__ cube,
+	const uint8_t* __restrict__ mask, int round)
+{
+	__shared__ double sc[5][6];
+	__shared__ double wT[4][64];
+	__shared__ __align__(16) double R[2][64][4];
+	__shared__ __align__(16) double ltab[128][4];
+	const int slot = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+	const FfiCtl& c = ws.ctl[b];
+	if (c.all_masked || c.no_good_mesh) return;
+	const int tile = P.ringtile_id[slot];
+	const int ty = tile / P.nx, tx = tile % P.nx;
+	const int lc = tid & 63, row0 = (tid >> 6) * 16, ox = lc >> 5;
+	const size_t img = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE + lc;
+	const int* __restrict__ idxmap = P.ringtile_idx + (size_t)slot * TBK_NPIX_TILE + lc;
+	// the loads of the first four rows are issued before the staging of the zoom rows
+	int id[4]; uint8_t mk[4]; float px[4];
+	auto load_rows = [&](int r0) {
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int lrow = r0 + j;
+			id[j] = __ldg(idxmap + lrow * TBK_TILE);
+			const size_t off = img + (size_t)lrow * P.W;
+			mk[j] = __ldg(mask + off);
+			px[j] = __ldg(cube + off);
+		}
+	};
+	load_rows(row0);
+	reinterpret_cast<double2*>(&ltab[0][0])[tid] = reinterpret_cast<const double2*>(&tbk_log10_tab[0][0])[tid];
+	if (round > 0) {
+		const double* coef = ws.coef + (size_t)b * P.ntiles;
+		if (tid < 25) sc[tid / 5][tid % 5] = coef[reflect_fold(ty - 2 + tid / 5, P.ny) * P.nx + reflect_fold(tx - 2 + tid % 5, P.nx)];
+		wT[tid & 3][tid >> 2] = __ldg(P.zoom_w + tid);
+		__syncthreads();
+		for (int e = tid; e < 64 * 5; e += 256) {
+			const int row = e & 63, B = e >> 6, oy = row >> 5;
+			double r = 0.0;
+#pragma unroll
+			for (int a = 0; a < 4; ++a) r = fma(wT[a][row], sc[oy + a][B], r);
+			if (B < 4) R[0][row][B] = r;
+			if (B > 0) R[1][row][B - 1] = r;
+		}
+	}
+	__syncthreads();
+	const double zp = c.zp, mmin = c.mesh_min, mmax = c.mesh_max;
+	const float zp32 = (float)c.zp;
+	const bool mconst = c.mesh_const != 0;
+	double* __restrict__ dst = ws.ring_v + (size_t)b * P.nringpix;
+	double wx[4] = {0.0, 0.0, 0.0, 0.0};
+	if (round > 0) {
+#pragma unroll
+		for (int a = 0; a < 4; ++a) wx[a] = wT[a][lc];
+	}
+#pragma unroll 1
+	for (int g = 0; g < 4; ++g) {
+		int cid[4]; uint8_t cmk[4]; float cpx[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { cid[j] = id[j]; cmk[j] = mk[j]; cpx[j] = px[j]; }
+		if (g < 3) load_rows(row0 + 4 * (g + 1));
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (cid[j] < 0) continue;
+			double val = nan_d();
+			if (!cmk[j]) {
+				if (round == 0) {
+					const float s = (cpx[j] + 0.0f) + zp32;
+					val = (double)(float)tbk_log10((double)s, ltab);
+				} else {
+					const int lrow = row0 + 4 * g + j;
+					const double2 ra = *reinterpret_cast<const double2*>(&R[ox][lrow][0]);
+					const double2 rb = *reinterpret_cast<const double2*>(&R[ox][lrow][2]);
+					const double acc = wx[0] * ra.x + wx[1] * ra.y + wx[2] * rb.x + wx[3] * rb.y;
+					const double sq = mconst ? mmin : clamp_d(acc, mmin, mmax);
+					val = tbk_log10(((double)cpx[j] - sq) + zp, ltab);
+				}
+			}
+			dst[cid[j]] = val;
+		}
+	}
+}
+
 __global__ void k_debug_log10(const double* __restrict__ in, double* __restrict__ out, int n)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2407,7 +2493,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 				LAUNCH(TBK_K_MISC, (k_set_zp<<<gb, 128, 0, st>>>(ws, B)));
 			}
 			if (tile_kernel == 0) LAUNCH(TBK_K_RING_GATHER, (k_ring_gather<<<dim3((P.nringpix + 255) / 256, B), 256, 0, st>>>(P, ws, cube, mask, round)));
-			else LAUNCH(TBK_K_RING_GATHER, (k_ring_gather_t<<<dim3(P.n_ringtiles, B), 256, 0, st>>>(P, ws, cube, mask, round)));
+			else if (tile_kernel == 3) LAUNCH(TBK_K_RING_GATHER, (k_ring_gather_t<<<dim3(P.n_ringtiles, B), 256, 0, st>>>(P, ws, cube, mask, round)));
+			else LAUNCH(TBK_K_RING_GATHER, (k_ring_gather_d<<<dim3(P.n_ringtiles, B), 256, 0, st>>>(P, ws, cube, mask, round)));
 			LAUNCH(TBK_K_RING_KDE, (k_ring_kde<<<dim3(B, P.nrings), TBK_KDE_NT, sizeof(KdeSmem), st>>>(P, ws)));
 			LAUNCH(TBK_K_RADIAL_FIT, (k_radial_fit<<<B, 32, 0, st>>>(P, ws, status, round, B)));
 			if (P.n_nonflat > 0) {
