@@ -360,10 +360,10 @@ def run_b200(args):
 	dom = max((k for k in prof if k not in ('misc', 'fallback')), key=lambda k: prof[k])
 	# launches per tbk_fit_batch and class (3 rounds): zone statistics of the raw pixels; per round producer + finish for the
 	# residuals; 'fallback' = the bucketed kernels for the queued meshes (1 + 3; on a side stream outside the profiled call)
-	launches_per_call = {'tile_base': 1, 'tile_round': 6, 'fallback': 4, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
+	launches_per_call = {'tile_base': 1, 'tile_round': 6, 'fallback': 5, 'zp_min': 4, 'ring_gather': 3, 'ring_kde': 3, 'radial_fit': 3, 'mesh': 3, 'final': 1}
 	dom_launch_ms = prof[dom] / (ncalls * launches_per_call.get(dom, 1))
 	peak, peak_src = load_peaks()
-	# The fit is a chain of ~32 kernel launches per batch and no single kernel dominates (the largest is < 30 % of
+	# The fit is a chain of ~33 kernel launches per batch and no single kernel dominates (the largest is < 30 % of
 	# the step), so the roofline is stated for the whole chain: algorithmic bytes of one tbk_fit_batch launch
 	# (37,748,736 B x FFIs per launch) over the summed device time of its kernels (CUDA events between the
 	# launches, tbk_fit_batch_profiled).  The dominant kernel is reported beside it with its share of the step.

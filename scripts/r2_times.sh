@@ -2,7 +2,7 @@
 # per-launch durations of one fit batch (default 64 FFIs): ncu time-only pass
 mkdir -p gpurun_out
 N=${1:-64}
-timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct --clock-control none -k regex:"^k_" -s 32 -c 32 --csv --log-file gpurun_out/times.csv python scripts/prof_run.py $N > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct --clock-control none -k regex:"^k_" -s 33 -c 33 --csv --log-file gpurun_out/times.csv python scripts/prof_run.py $N > /dev/null 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/times.csv')) if len(r)>10]
