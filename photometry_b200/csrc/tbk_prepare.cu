@@ -35,9 +35,96 @@ __global__ void __launch_bounds__(256) k_time_smooth(size_t npix4, const float4*
 	out[(size_t)k * npix4 + p] = o;
 }
 
+// The same result with every frame read once: a thread owns a few horizontally adjacent pixels and walks a segment of the
+// cadence axis with the 2w+1 frames of the window in registers (a ring buffer with compile-time slots: the walk is unrolled
+// by the window length).  Every output is still summed from scratch over its window in index order, in float32, so the
+// result is bit-identical to k_time_smooth; what changes is the traffic -- 1 read + 1 write per frame instead of 2w+1 reads
+// (the L2 only partly absorbs those: 14 us per FFI at w = 4 and 33 us at w = 13 against 8 us at w = 1).
+template <typename V> struct SmoothVec;
+template <> struct SmoothVec<float4> {
+	static constexpr int N = 4;
+	__device__ static __forceinline__ float get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+	__device__ static __forceinline__ float4 make(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
+	__device__ static __forceinline__ float4 nanv() { const float q = nan_f(); return make_float4(q, q, q, q); }
+};
+template <> struct SmoothVec<float2> {
+	static constexpr int N = 2;
+	__device__ static __forceinline__ float get(const float2& v, int i) { return i == 0 ? v.x : v.y; }
+	__device__ static __forceinline__ float2 make(const float* a) { return make_float2(a[0], a[1]); }
+	__device__ static __forceinline__ float2 nanv() { const float q = nan_f(); return make_float2(q, q); }
+};
+
+template <int WH, typename V, int SEG>
+__global__ void __launch_bounds__(256) k_time_smooth_slide(size_t npixv, const V* __restrict__ bkg, int n,
+	const V* __restrict__ halo_lo, int n_lo, const V* __restrict__ halo_hi, int n_hi, V* __restrict__ out)
+{
+	constexpr int L = 2 * WH + 1;
+	typedef SmoothVec<V> SV;
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npixv) return;
+	const int k_lo = blockIdx.y * SEG, k_hi = min(n, k_lo + SEG);
+	// frame j of the (halo-extended) stack; frames that do not exist read as NaN, which the nan-mean skips
+	auto frame = [&](int j) -> V {
+		if (j < 0) return (n_lo + j >= 0) ? __ldg(halo_lo + (size_t)(n_lo + j) * npixv + p) : SV::nanv();
+		if (j >= n) return (j - n < n_hi) ? __ldg(halo_hi + (size_t)(j - n) * npixv + p) : SV::nanv();
+		return __ldg(bkg + (size_t)j * npixv + p);
+	};
+	// ring of L + D slots: the frame a step adds to its window was requested D steps earlier
+	constexpr int D = 2, R = L + D;
+	V buf[R];
+#pragma unroll
+	for (int u = 0; u < 2 * WH + D; ++u) buf[u] = frame(k_lo - WH + u);
+	for (int k = k_lo; k < k_hi; k += R) {
+#pragma unroll
+		for (int u = 0; u < R; ++u) {
+			const int kk = k + u;
+			if (kk < k_hi) {
+				buf[(2 * WH + D + u) % R] = frame(kk + WH + D);
+				float o[SV::N];
+#pragma unroll
+				for (int c = 0; c < SV::N; ++c) {
+					// frames kk - w .. kk + w in index order.  Without a NaN in the window the nan-mean is the plain sequential
+					// sum (the same additions in the same order) over L; a NaN result sends the pixel through the NaN-aware sum
+					float sum = 0.f; int cnt = L;
+#pragma unroll
+					for (int t = 0; t < L; ++t) sum += SV::get(buf[(u + t) % R], c);
+					if (!(sum == sum)) {
+						sum = 0.f; cnt = 0;
+#pragma unroll
+						for (int t = 0; t < L; ++t) nanacc(SV::get(buf[(u + t) % R], c), sum, cnt);
+					}
+					o[c] = cnt ? sum / (float)cnt : nan_f();
+				}
+				out[(size_t)kk * npixv + p] = SV::make(o);
+			}
+		}
+	}
+}
+
+template <int WH, typename V, int SEG>
+static void launch_smooth_slide(size_t npix, const float* bkg, int n, const float* halo_lo, int n_lo, const float* halo_hi, int n_hi,
+	float* out, cudaStream_t st)
+{
+	const size_t npixv = npix / SmoothVec<V>::N;
+	dim3 grid((unsigned)((npixv + 255) / 256), (unsigned)((n + SEG - 1) / SEG));
+	k_time_smooth_slide<WH, V, SEG><<<grid, 256, 0, st>>>(npixv, (const V*)bkg, n, (const V*)halo_lo, n_lo, (const V*)halo_hi, n_hi, (V*)out);
+}
+
 int tbk_launch_time_smooth(int H, int W, const float* bkg, int n, int w,
 	const float* halo_lo, int n_lo, const float* halo_hi, int n_hi, float* out, cudaStream_t st)
 {
+	// the windows of the TESS cadences (prepare.py:258 and the 200-s extension) walk the cadence axis; any other w, or
+	// TBK_SMOOTH_KERNEL=0, takes the frame-parallel kernel
+	static const bool slide = !(getenv("TBK_SMOOTH_KERNEL") && atoi(getenv("TBK_SMOOTH_KERNEL")) == 0);
+	if (slide && n > 0 && (w == 1 || w == 4 || w == 13)) {
+		const size_t npix = (size_t)H * W;
+		if (w == 1) launch_smooth_slide<1, float4, 128>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);
+		else if (w == 4) launch_smooth_slide<4, float4, 128>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);
+		else launch_smooth_slide<13, float2, 256>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { tbk_set_error("k_time_smooth_slide: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+		return TBK_OK;
+	}
 	const size_t npix4 = (size_t)H * W / 4;
 	dim3 grid(n, (unsigned)((npix4 + 255) / 256));
 	k_time_smooth<<<grid, 256, 0, st>>>(npix4, (const float4*)bkg, n, w, (const float4*)halo_lo, n_lo,

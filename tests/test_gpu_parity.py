@@ -171,13 +171,36 @@ def test_time_smooth_bit_exact_and_sharded():
 	bkg[5, 3, 3] = np.nan; bkg[4:7, 9, 9] = np.nan
 	fit = pb.BackgroundFitter((H, W))
 	t = torch.from_numpy(bkg).cuda()
-	for w in (1, 4):
+	for w in (1, 2, 4):   # 1 and 4 walk the cadence axis with the window in registers, 2 takes the frame-parallel kernel
 		ref = oracle.time_smooth_backgrounds(bkg, 2 * w + 1)
 		full = fit.time_smooth(t, w).cpu().numpy()
 		np.testing.assert_array_equal(full, ref)
 		lo = fit.time_smooth(t[:6], w, None, t[6:6 + w]).cpu().numpy()
 		hi = fit.time_smooth(t[6:], w, t[6 - w:6], None).cpu().numpy()
 		np.testing.assert_array_equal(np.concatenate([lo, hi]), ref)
+
+
+@pytest.mark.gpu
+def test_time_smooth_long_stack_all_windows():
+	"""Stacks longer than one segment of the cadence walk, every window of the TESS cadences (w = 1, 4, 13), short halos."""
+	rng = np.random.default_rng(41)
+	n, H, W = 300, 64, 64
+	bkg = rng.normal(100, 2, (n, H, W)).astype('float32')
+	bkg[rng.uniform(size=bkg.shape) < 0.01] = np.nan
+	bkg[100:140, 2, 5] = np.nan   # a pixel whose whole window is NaN for a while
+	fit = pb.BackgroundFitter((H, W))
+	t = torch.from_numpy(bkg).cuda()
+	for w in (1, 4, 13):
+		ref = oracle.time_smooth_backgrounds(bkg, 2 * w + 1)
+		np.testing.assert_array_equal(fit.time_smooth(t, w).cpu().numpy(), ref)
+		cut = 131
+		lo = fit.time_smooth(t[:cut], w, None, t[cut:cut + w]).cpu().numpy()
+		hi = fit.time_smooth(t[cut:], w, t[cut - w:cut], None).cpu().numpy()
+		np.testing.assert_array_equal(np.concatenate([lo, hi]), ref)
+		# halos shorter than the window (a neighbour that holds only a few frames)
+		short = fit.time_smooth(t[:5], w, None, t[5:7]).cpu().numpy()
+		ref_short = oracle.time_smooth_backgrounds(bkg[:7], 2 * w + 1)[:5]
+		np.testing.assert_array_equal(short, ref_short)
 
 
 def test_sum_accumulate_matches_oracle():
