@@ -145,9 +145,14 @@ __global__ void __launch_bounds__(256) k_zero_detect(size_t npix4, const float4*
 {
 	const int k = blockIdx.y;
 	bool nz = false;
-	for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix4; p += (size_t)gridDim.x * blockDim.x) {
-		const float4 v = __ldg(cube + (size_t)k * npix4 + p);
-		nz |= !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
+	// a frame with data answers on the first load of any warp; only an all-zero frame is read to the end
+	for (size_t p0 = (size_t)blockIdx.x * blockDim.x; p0 < npix4; p0 += (size_t)gridDim.x * blockDim.x) {
+		const size_t p = p0 + threadIdx.x;
+		if (p < npix4) {
+			const float4 v = __ldg(cube + (size_t)k * npix4 + p);
+			nz |= !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
+		}
+		if (__any_sync(0xffffffffu, nz) || *((volatile int*)&zero_flags[k]) == 0) break;
 	}
 	if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) zero_flags[k] = 0;
 }
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(256) k_sum_accumulate(PlanDev P, const float4*
 	const int gx = (int)((p * 4) % P.W);
 	double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 	int n0 = 0, n1 = 0, n2 = 0, n3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-	for (int k = 0; k < n; ++k) {
+	auto step = [&](int k, uchar4 f, float4 x, const float4 bk) {
 		const tbk_ffi_meta m = meta[k];
 		bool excl_all = false, excl_cols = false;
 		if (P.is_tess) {
@@ -176,16 +181,11 @@ __global__ void __launch_bounds__(256) k_sum_accumulate(PlanDev P, const float4*
 			if (zero_flags[k]) excl_all = true;
 		}
 		const size_t o = (size_t)k * npix4 + p;
-		uchar4 f = flags[o];
 		if (excl_all || excl_cols) {
 			f.x |= 2; f.y |= 2; f.z |= 2; f.w |= 2;   // PixelQualityFlags.ManualExclude
 			flags[o] = f;
 		}
-		float4 x = __ldg(cube + o);
-		if (!m.backapp) {
-			const float4 bk = __ldg(bkg + o);
-			x.x -= bk.x; x.y -= bk.y; x.z -= bk.z; x.w -= bk.w;
-		}
+		if (!m.backapp) { x.x -= bk.x; x.y -= bk.y; x.z -= bk.z; x.w -= bk.w; }
 		if (f.x & 2) x.x = nan_f();
 		if (f.y & 2) x.y = nan_f();
 		if (f.z & 2) x.z = nan_f();
@@ -199,6 +199,23 @@ __global__ void __launch_bounds__(256) k_sum_accumulate(PlanDev P, const float4*
 			s3 += (x.w == x.w) ? (double)x.w : 0.0;
 		}
 		u0 += (f.x & 1) == 0; u1 += (f.y & 1) == 0; u2 += (f.z & 1) == 0; u3 += (f.w & 1) == 0;
+	};
+	// four cadences per trip: their twelve loads are in flight together (the walk is bound by memory latency otherwise); the
+	// cadences are still folded into the float64 sums one after the other, in index order
+	int k = 0;
+	for (; k + 4 <= n; k += 4) {
+		uchar4 f[4]; float4 x[4], bk[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const size_t o = (size_t)(k + u) * npix4 + p;
+			f[u] = flags[o]; x[u] = __ldg(cube + o); bk[u] = __ldg(bkg + o);
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) step(k + u, f[u], x[u], bk[u]);
+	}
+	for (; k < n; ++k) {
+		const size_t o = (size_t)k * npix4 + p;
+		step(k, flags[o], __ldg(cube + o), __ldg(bkg + o));
 	}
 	double* sp = sum + p * 4; int32_t* np_ = nimg + p * 4; int32_t* up = used + p * 4;
 	sp[0] += s0; sp[1] += s1; sp[2] += s2; sp[3] += s3;
