@@ -54,6 +54,13 @@ template <> struct SmoothVec<float2> {
 	__device__ static __forceinline__ float2 nanv() { const float q = nan_f(); return make_float2(q, q); }
 };
 
+template <> struct SmoothVec<float> {
+	static constexpr int N = 1;
+	__device__ static __forceinline__ float get(const float& v, int) { return v; }
+	__device__ static __forceinline__ float make(const float* a) { return a[0]; }
+	__device__ static __forceinline__ float nanv() { return nan_f(); }
+};
+
 template <int WH, typename V, int SEG>
 __global__ void __launch_bounds__(256) k_time_smooth_slide(size_t npixv, const V* __restrict__ bkg, int n,
 	const V* __restrict__ halo_lo, int n_lo, const V* __restrict__ halo_hi, int n_hi, V* __restrict__ out)
@@ -120,7 +127,7 @@ int tbk_launch_time_smooth(int H, int W, const float* bkg, int n, int w,
 		const size_t npix = (size_t)H * W;
 		if (w == 1) launch_smooth_slide<1, float4, 128>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);
 		else if (w == 4) launch_smooth_slide<4, float4, 128>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);
-		else launch_smooth_slide<13, float2, 256>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);
+		else launch_smooth_slide<13, float, 256>(npix, bkg, n, halo_lo, n_lo, halo_hi, n_hi, out, st);   // one pixel per thread: the unrolled walk of 29 steps stays within the instruction cache
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { tbk_set_error("k_time_smooth_slide: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
 		return TBK_OK;
