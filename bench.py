@@ -450,11 +450,11 @@ def run_b200(args):
 		np_ = min(n, args.prepare_ffis)
 		barrier()
 		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True)
+		pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, nstreams=args.streams)
 		barrier()
 		ptm = {}
 		g0.record()
-		res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, timings=ptm)
+		res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, timings=ptm, nstreams=args.streams)
 		g1.record()
 		barrier()
 		pms = g0.elapsed_time(g1)
