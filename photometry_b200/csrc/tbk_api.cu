@@ -52,7 +52,7 @@ struct tbk_plan {
 // Byte offsets of the workspace sections for a batch of B (a value, not plan state: a plan may serve several streams
 // and host threads with different batch sizes at once).
 struct WsLayout {
-	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb, off_idwbits, off_idwtab, off_rtab, off_fb2, off_zrec;
+	size_t off_ctl, off_base, off_nf, off_coef, off_mesh, off_s2raw, off_s2hist, off_ringv, off_sbmin, off_sblow, off_fb, off_idwbits, off_idwtab, off_rtab, off_fb2, off_zrec, off_rt;
 	size_t total;
 };
 
@@ -118,6 +118,7 @@ static WsLayout layout(const tbk_plan* plan, int B)
 	p->off_rtab = o;   o = align_up(o + sizeof(double) * 8 * (size_t)B * TBK_RSUB * std::max(P.nrings - 1, 1));
 	p->off_fb2 = o;    o = align_up(o + sizeof(int) * (size_t)B * std::max(P.n_nonflat, 1));
 	p->off_zrec = o;   o = align_up(o + ZR_REC_BYTES * (size_t)B * std::max(P.n_nonflat, 1));
+	p->off_rt = o;     o = align_up(o + sizeof(int) * (size_t)B * P.ntiles);
 	L.total = o;
 	return L;
 }
@@ -145,6 +146,7 @@ static Workspace carve(const tbk_plan* plan, void* base, int B)
 	ws.rtab = (double*)(b + p->off_rtab);
 	ws.fb_list2 = (int*)(b + p->off_fb2);
 	ws.zrec = (unsigned char*)(b + p->off_zrec);
+	ws.rt_list = (int*)(b + p->off_rt);
 	return ws;
 }
 

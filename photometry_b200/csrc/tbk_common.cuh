@@ -104,6 +104,7 @@ struct Workspace {
 	unsigned char* zrec;    // [B][n_nonflat][ZR_REC_BYTES] lists of the residual statistics (ZoneRec + tails + zone)
 	double* rtab;           // [B][TBK_RSUB * max(nrings - 1, 1)][8] radial profile as Taylor pieces (see RadialTab)
 	int* fb_list2;          // [B * n_nonflat] queue of the residual statistics (entries b * n_nonflat + slot)
+	int* rt_list;           // [B * ntiles] retry queue of the raw-pixel statistics (entries b * ntiles + tile, count in fb_count[8])
 	uint32_t* idw_bits;     // [B][1 + ceil(ntiles / 32)] valid flag + good-mesh bitmap the neighbour table was built for
 	uint16_t* idw_tab;      // [B][ntiles][10] IDW neighbours (mesh ids, 0xFFFF = none) of the excluded meshes
 	int* fb_count;          // [1] meshes queued for the full-buffer statistics

@@ -329,11 +329,11 @@ struct ZbStage {
 	float px[ZB_WARPS][TBK_NPIX_TILE];
 	unsigned long long bar[ZB_WARPS];
 };
-// RETRY = true: the launch works off the retry queue (ws.fb_list2 during the raw-pixel phase, count in fb_count[8]); a
+// RETRY = true: the launch works off the retry queue (ws.rt_list, count in fb_count[8]); a
 // warp takes queue entry blockIdx.x * ZB_WARPS + w, the plan comes from the statistics parked in the mesh's TileStat.
 template <bool HAS_EXTRA, bool STAGED, bool RETRY>
 __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(PlanDev P, Workspace ws,
-	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out, int B)
+	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out, int rt_cap)
 {
 	__shared__ ZoneSmem<Zn32> smw[ZB_WARPS];
 	extern __shared__ __align__(128) unsigned char zb_dyn[];
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 	int tile = blockIdx.x * ZB_WARPS + w, b = blockIdx.y;
 	if (RETRY) {
 		const int e = blockIdx.x * ZB_WARPS + w;
-		if (e >= min(ws.fb_count[8], B * P.n_nonflat)) return;
-		const int ent = ws.fb_list2[e];
+		if (e >= min(ws.fb_count[8], rt_cap)) return;
+		const int ent = ws.rt_list[e];
 		b = ent / P.ntiles; tile = ent % P.ntiles;
 	}
 	if (tile >= P.ntiles) return;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 			bool retry = false;
 			if (!RETRY && why == ZN_WHY_BOUND && st.std > 0.0) {
 				const int pos = atomicAdd(ws.fb_count + 8, 1);
-				if (pos < B * P.n_nonflat) { *dst = st; ws.fb_list2[pos] = b * P.ntiles + tile; retry = true; }
+				if (pos < rt_cap) { *dst = st; ws.rt_list[pos] = b * P.ntiles + tile; retry = true; }
 			}
 			if (!retry) { ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile; atomicAdd(ws.fb_count + 16 + why, 1); }
 		}
@@ -2449,6 +2449,7 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 	else if (tile_kernel == 3) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_w3<false, 2><<<gt, 64, 0, st>>>(P, ws, cube, extra, mask)));
 	else {
 		const dim3 gz((P.ntiles + ZB_WARPS - 1) / ZB_WARPS, B);
+		const int rt_cap = std::min(B * P.ntiles, std::max(B * P.ntiles / 8, 64));   // retry queue: up to an eighth of the meshes
 		if (tile_kernel == 7) {
 			// measured alternative: mesh staged in shared memory by TMA bulk copies
 			static bool attr_set = false;
@@ -2457,21 +2458,22 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 				cudaFuncSetAttribute(k_tile_base_z<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbStage));
 				attr_set = true;
 			}
-			if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, true, false><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask, B)));
-			else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, true, false><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask, B)));
+			if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, true, false><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask, rt_cap)));
+			else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, true, false><<<gz, 32 * ZB_WARPS, sizeof(ZbStage), st>>>(P, ws, cube, extra, mask, rt_cap)));
 		}
-		else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask, B)));
-		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask, B)));
+		else if (extra) LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<true, false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask, rt_cap)));
+		else LAUNCH(TBK_K_TILE_BASE, (k_tile_base_z<false, false, false><<<gz, 32 * ZB_WARPS, 0, st>>>(P, ws, cube, extra, mask, rt_cap)));
 		// the queued meshes (bucketed statistics) are only needed by k_mesh_finalize: side stream, joined before round 0's
 		cudaStream_t fs = st;
 		if (side && !prof) { fs = side->stream; cudaEventRecord(side->fork, st); cudaStreamWaitEvent(fs, side->fork, 0); base_forked = true; }
 		{
-			// second run of the zone kernel for the meshes whose first plan put a clip bound inside the bulk (queue capacity
-			// B * n_nonflat entries, one warp per entry; warps beyond the queue length leave at once)
-			const dim3 gr((B * P.n_nonflat + ZB_WARPS - 1) / ZB_WARPS, 1);
+			// second run of the zone kernel for the meshes whose first plan put a clip bound inside the bulk: one warp per queue
+			// entry, warps beyond the queue length leave at once; the queue holds up to an eighth of the meshes, more go to the
+			// bucketed path
+			const dim3 gr((rt_cap + ZB_WARPS - 1) / ZB_WARPS, 1);
 			if (gr.x > 0) {
-				if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<true, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, B)));
-				else LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<false, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, B)));
+				if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<true, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
+				else LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<false, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
 			}
 		}
 		if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<true><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
