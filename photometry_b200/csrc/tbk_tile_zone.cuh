@@ -13,10 +13,12 @@
 //     [ZL, ZH] around it (a few per cent again) are kept one by one, together with the exact number of elements
 //     below ZL, so a rank inside the zone is resolved exactly from a small counting sort.
 // Pass 1 (mask, minima, counts, bulk moments) streams the mesh from HBM, pass 2 (collect tails + zone) re-reads it from
-// L2.  Anything the two lists cannot answer exactly -- a bound that enters the bulk, a median rank outside the zone, a
-// list overflow, a degenerate sample, a sparsely populated mesh -- sends the mesh to a queue that the bucketed kernels
-// (tbk_tile_warp.cuh) work off afterwards.  The result of a mesh that does not fall back is exactly the reference's:
-// the same membership decisions on the same float64 comparisons, exact medians, float64 moments.
+// L2.  A clip bound that enters the bulk (the sample overestimated the width) re-plans the mesh around the exact statistics
+// of the failing iteration: one more run for the raw-pixel kernel, the previous round's width for the residual kernel.
+// Anything the two lists still cannot answer exactly -- a median rank outside the zone, a list overflow, a degenerate
+// sample, a sparsely populated mesh -- sends the mesh to a queue that the bucketed kernels (tbk_tile_warp.cuh) work off
+// afterwards.  The result of a mesh that does not fall back is exactly the reference's: the same membership decisions on
+// the same float64 comparisons, exact medians, float64 moments.
 #pragma once
 #include "tbk_tile_warp.cuh"
 
