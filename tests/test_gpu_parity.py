@@ -279,6 +279,22 @@ def test_full_size_properties(full_stack):
 	assert float(bkg.min()) > 0 and float(bkg.max()) < 8e4
 
 
+def test_repeat_run_bit_identical(full_stack):
+	"""
+	Nothing in the chain depends on timing: the fallback and retry queues are filled in arbitrary order but every mesh is
+	evaluated on its own, the KDE bins fixed-point sums, the tail / zone lists are ballot-ordered.  Two runs give the same bits,
+	on the caller's stream alone and with the chunks spread over several streams.
+	"""
+	cube, hdrs, fit, bkg, mask, st = full_stack
+	meta = pb.meta_from_headers(hdrs)
+	b1, m1, _ = fit.fit(cube, meta)
+	assert torch.equal(b1, bkg) and torch.equal(m1, mask)
+	b2 = torch.empty_like(cube); m2 = torch.empty(cube.shape, dtype=torch.uint8, device=cube.device)
+	fit.fit_stack(cube, fit.meta_to_device(meta), b2, m2, chunk=2, nstreams=3)
+	torch.cuda.synchronize()
+	assert torch.equal(b2, bkg) and torch.equal(m2, mask)
+
+
 # ---- independent implementations agree --------------------------------------------------------
 VARIANTS = ('0', '3', '6', '7')
 
