@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(32 * NW, 20 / NW) k_tile_base_w3(PlanDev P, Wo
 // The per-pixel bodies are written as predicated PTX: the compiler's own if-conversion of the C++ form spends ~1.7x
 // the instructions (select-based counters, recomputed predicates, per-append address arithmetic).
 #define ZB_WARPS 4
+#define ZB_RETRY_TCAP 136   // tail elements per lane in the retry launch (a lane sees 128 pixels of its mesh)
 
 // Pass 1, one pixel.  k = float bits of x (x >= +0 when valid), ex = extra-mask byte (0 = usable).
 //   valid  = k <= cut && !ex;  kv = valid ? k : +inf key;  mask byte Q set when !valid;  smin = min(smin, kv)
@@ -335,18 +336,20 @@ template <bool HAS_EXTRA, bool STAGED, bool RETRY>
 __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(PlanDev P, Workspace ws,
 	const float* __restrict__ cube, const uint8_t* __restrict__ extra, uint8_t* __restrict__ mask_out, int rt_cap)
 {
-	__shared__ ZoneSmem<Zn32> smw[ZB_WARPS];
+	// the retry launch runs one warp per CTA with tail lists long enough for any mesh (128 pixels per lane)
+	constexpr int TCAP = RETRY ? ZB_RETRY_TCAP : ZN_TCAP, NW = RETRY ? 1 : ZB_WARPS;
+	__shared__ ZoneSmem<Zn32, TCAP> smw[NW];
 	extern __shared__ __align__(128) unsigned char zb_dyn[];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	int tile = blockIdx.x * ZB_WARPS + w, b = blockIdx.y;
 	if (RETRY) {
-		const int e = blockIdx.x * ZB_WARPS + w;
+		const int e = blockIdx.x;
 		if (e >= min(ws.fb_count[8], rt_cap)) return;
 		const int ent = ws.rt_list[e];
 		b = ent / P.ntiles; tile = ent % P.ntiles;
 	}
 	if (tile >= P.ntiles) return;
-	ZoneSmem<Zn32>& sm = smw[w];
+	ZoneSmem<Zn32, TCAP>& sm = smw[w];
 	const int ty = tile / P.nx, tx = tile % P.nx;
 	FfiCtl& c = ws.ctl[b];
 	const size_t tile0 = (size_t)b * P.H * P.W + (size_t)(ty * TBK_TILE) * P.W + tx * TBK_TILE;
@@ -393,9 +396,9 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 	ZonePlan zp;
 	zp.ok = false; zp.mhat = 0.0; zp.shat = 1.0; zp.pivot = 0.0; zp.A = 0.0; zp.B = 0.0;
 	if (RETRY) {
-		const TileStat pv = ws.tile_base[(size_t)b * P.ntiles + tile];
-		zp.ok = pv.std > 0.0; zp.mhat = pv.med; zp.shat = 0.75 * pv.std; zp.pivot = Zn32::pivot_of(zp.mhat);
-		zp.A = zp.mhat - ZN_CT * zp.shat; zp.B = zp.mhat + ZN_CT * zp.shat;   // median -+ 1.5 sigma of the failing iteration: half its clip range
+		const TileStat pv = ws.tile_base[(size_t)b * P.ntiles + tile];   // the plan of the retry, parked by the first run
+		zp.ok = pv.std > 0.0; zp.mhat = pv.med; zp.shat = pv.std; zp.pivot = Zn32::pivot_of(zp.mhat);
+		zp.A = zp.mhat - ZN_CT * zp.shat; zp.B = zp.mhat + ZN_CT * zp.shat;
 	} else if (do_stats) {
 		uint32_t sk[2];
 #pragma unroll
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 	const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(&sm.tails[lane]);
 	const uint32_t zbase = (uint32_t)__cvta_generic_to_shared(&sm.zone[lane]);
 	uint32_t tptr = tbase;
-	const uint32_t tend = do_stats ? tbase + 128u * ZN_TCAP : tbase;
+	const uint32_t tend = do_stats ? tbase + 128u * TCAP : tbase;
 
 	// ---- pass 1: mask, flags, sub-block minima, counts, bulk moments, tails
 	uint32_t nz = 0u, kmin = TW_INVALID;
@@ -554,13 +557,20 @@ __global__ void __launch_bounds__(32 * ZB_WARPS, STAGED ? 2 : 5) k_tile_base_z(P
 	if (lane == 0) {
 		if (good) *dst = st;
 		else {
-			// A clip bound that entered the bulk (the 64-pixel sample overestimated the width: star wings, gradients) does not
-			// send the mesh to the bucketed path straight away: the statistics of the failing iteration are exact, so the mesh
-			// is queued for ONE more run of this kernel (RETRY) with the bulk placed around them; they travel in *dst.
+			// Two failures get ONE more run of this kernel (RETRY) before the bucketed path; the plan of that run travels in *dst.
+			//  * a clip bound entered the bulk (the 64-pixel sample overestimated the width: star wings, gradients): the
+			//    statistics of the failing iteration are exact, the bulk is placed around them (median -+ 1.5 sigma of that
+			//    iteration, half its clip range);
+			//  * a tail list overflowed (crowded meshes: a quarter of the pixels above the bulk): the same plan again -- the retry
+			//    launch has room for every pixel of the mesh in its tail lists.
 			bool retry = false;
-			if (!RETRY && why == ZN_WHY_BOUND && st.std > 0.0) {
+			if (!RETRY && zp.ok && ((why == ZN_WHY_BOUND && st.std > 0.0) || why == ZN_WHY_LIST)) {
 				const int pos = atomicAdd(ws.fb_count + 8, 1);
-				if (pos < rt_cap) { *dst = st; ws.rt_list[pos] = b * P.ntiles + tile; retry = true; }
+				if (pos < rt_cap) {
+					if (why == ZN_WHY_BOUND) st.std = 0.75 * st.std;
+					else { st.med = zp.mhat; st.std = zp.shat; }
+					*dst = st; ws.rt_list[pos] = b * P.ntiles + tile; retry = true;
+				}
 			}
 			if (!retry) { ws.fb_list[atomicAdd(ws.fb_count, 1)] = b * P.ntiles + tile; atomicAdd(ws.fb_count + 16 + why, 1); }
 		}
@@ -2470,10 +2480,10 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 			// second run of the zone kernel for the meshes whose first plan put a clip bound inside the bulk: one warp per queue
 			// entry, warps beyond the queue length leave at once; the queue holds up to an eighth of the meshes, more go to the
 			// bucketed path
-			const dim3 gr((rt_cap + ZB_WARPS - 1) / ZB_WARPS, 1);
+			const dim3 gr(rt_cap, 1);
 			if (gr.x > 0) {
-				if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<true, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
-				else LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<false, false, true><<<gr, 32 * ZB_WARPS, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
+				if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<true, false, true><<<gr, 32, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
+				else LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<false, false, true><<<gr, 32, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
 			}
 		}
 		if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<true><<<592, 64, 0, fs>>>(P, ws, cube, extra)));

@@ -57,9 +57,9 @@ struct Zn64 : TwF64 {
 	__device__ static __forceinline__ Range range(double lo, double hi) { Range r; r.tlo = lo; r.thi = hi; return r; }
 };
 
-template <typename T>
+template <typename T, int TCAP = ZN_TCAP>
 struct ZoneSmem {
-	typename T::Raw tails[ZN_TCAP * 32];   // pass 2: per-lane lists [j * 32 + lane]; then dense
+	typename T::Raw tails[TCAP * 32];   // pass 2: per-lane lists [j * 32 + lane]; then dense
 	typename T::K zone[ZN_ZCAP * 32];      // pass 2: per-lane lists of Raw (same size as K); then bin-sorted keys
 	uint32_t cnt[ZN_BINS];                 // zone bin counts -> starts -> ends
 };
@@ -265,15 +265,15 @@ __device__ bool zone_iterate(TailAt tail_at, const typename T::K* zone, int lane
 
 // Finish from per-lane lists in shared memory (the fused raw-pixel kernel).  tcnt / zcnt: this lane's list lengths;
 // zl / zscale: zone bin map; the other arguments are warp-uniform.
-template <typename T>
-__device__ bool zone_finish(ZoneSmem<T>& sm, int lane, int n, int nA, int nB, int nZL, int tcnt, int zcnt,
+template <typename T, int TCAP>
+__device__ bool zone_finish(ZoneSmem<T, TCAP>& sm, int lane, int n, int nA, int nB, int nZL, int tcnt, int zcnt,
 	double s1b, double s2b, double pivot, double vA, double vB, typename T::Raw zl, float zscale, TileStat& out, int& why)
 {
 	typedef typename T::Raw Raw;
 	out.mean = out.med = out.std = nan_d();
 	out.nfin = 0; out.pad = 0;
 	if (n - nA - nB <= 0) { why = ZN_WHY_EMPTY; return false; }
-	if (__any_sync(0xffffffffu, tcnt > ZN_TCAP || zcnt > ZN_ZCAP)) { why = ZN_WHY_LIST; return false; }
+	if (__any_sync(0xffffffffu, tcnt > TCAP || zcnt > ZN_ZCAP)) { why = ZN_WHY_LIST; return false; }
 	const int nT = nA + nB;
 	const int nZ = __reduce_add_sync(0xffffffffu, zcnt);
 	if (nZ == 0) { why = ZN_WHY_EMPTY; return false; }
