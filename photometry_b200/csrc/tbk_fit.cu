@@ -2486,8 +2486,8 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 				else LAUNCH(TBK_K_FALLBACK, (k_tile_base_z<false, false, true><<<gr, 32, 0, fs>>>(P, ws, cube, extra, mask, rt_cap)));
 			}
 		}
-		if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<true><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
-		else LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<false><<<592, 64, 0, fs>>>(P, ws, cube, extra)));
+		if (extra) LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<true><<<1184, 64, 0, fs>>>(P, ws, cube, extra)));
+		else LAUNCH(TBK_K_FALLBACK, (k_tile_base_fb<false><<<1184, 64, 0, fs>>>(P, ws, cube, extra)));
 		if (base_forked) cudaEventRecord(side->join, fs);
 	}
 	LAUNCH(TBK_K_MISC, (k_post_base<<<gb, 128, 0, st>>>(P, ws, status, B)));
@@ -2518,7 +2518,7 @@ int tbk_launch_fit(const PlanDev& P, const Workspace& ws, const float* cube, int
 					// the queued meshes are only needed by this round's k_mesh_finalize: side stream, joined there
 					cudaStream_t fs = st;
 					if (side && !prof) { fs = side->stream; cudaEventRecord(side->fork, st); cudaStreamWaitEvent(fs, side->fork, 0); base_forked = true; }
-					LAUNCH(TBK_K_FALLBACK, (k_tile_round_w<true><<<296, 128, 0, fs>>>(P, ws, cube, mask, round)));
+					LAUNCH(TBK_K_FALLBACK, (k_tile_round_w<true><<<740, 128, 0, fs>>>(P, ws, cube, mask, round)));
 					if (fs != st) cudaEventRecord(side->join, fs);
 				}
 			}
