@@ -126,6 +126,15 @@ int tbk_sum_accumulate(tbk_plan* plan, const float* cube, const float* bkg_smoot
 	uint8_t* flags, const tbk_ffi_meta* meta, int n, float* flux_out,
 	double* sum, int32_t* nimg, int32_t* used, void* stream);
 
+/*
+ * Transport format of the mask for host-resident results (the device-to-host link bounds the end-to-end path and the mask
+ * is a fifth of the result bytes): tbk_pack_mask turns nbytes mask bytes (device, nbytes % 32 == 0) into nbytes / 8 bytes
+ * of bits, bit (7 - j) of byte i = mask[8 i + j] != 0 (the order of numpy.packbits); tbk_unpack_mask_host expands
+ * nbits_bytes such bytes into 0 / 1 bytes on the calling CPU thread (host pointers).
+ */
+int tbk_pack_mask(const uint8_t* mask, size_t nbytes, uint8_t* bits, void* stream);
+int tbk_unpack_mask_host(const uint8_t* bits, size_t nbits_bytes, uint8_t* out);
+
 /* prepare.py:459,468: sumimage = sum / nimg (0/0 -> NaN); pixels_used = used / numfiles > threshold. */
 int tbk_sum_finalize(tbk_plan* plan, const double* sum, const int32_t* nimg, const int32_t* used,
 	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, void* stream);

@@ -46,6 +46,8 @@ SIGNATURES = {
 	'tbk_fit_batch': (C.c_int, [_p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p]),
 	'tbk_time_smooth': (C.c_int, [_p, _p, C.c_int, C.c_int, _p, C.c_int, _p, C.c_int, _p, _p]),
 	'tbk_sum_accumulate': (C.c_int, [_p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p]),
+	'tbk_pack_mask': (C.c_int, [_p, C.c_size_t, _p, _p]),
+	'tbk_unpack_mask_host': (C.c_int, [_p, C.c_size_t, _p]),
 	'tbk_sum_finalize': (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_double, _p, _p, _p]),
 	'tbk_debug_fetch': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
 	'tbk_bkgshe_indicator': (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),

@@ -439,6 +439,24 @@ extern "C" int tbk_sum_accumulate(tbk_plan* p, const float* cube, const float* b
 	return rc;
 }
 
+extern "C" int tbk_pack_mask(const uint8_t* mask, size_t nbytes, uint8_t* bits, void* stream)
+{
+	if (!mask || !bits || (nbytes % 32) != 0 || (((uintptr_t)mask) & 15) || (((uintptr_t)bits) & 3)) { tbk_set_error("tbk_pack_mask: bad argument (nbytes must be a multiple of 32, mask 16-byte aligned)"); return TBK_ERR_INVALID; }
+	return tbk_launch_pack_mask(mask, nbytes, bits, (cudaStream_t)stream);
+}
+
+// host side of the same format: out[8 i + j] = bit (7 - j) of bits[i] (0 / 1 bytes); runs on the calling CPU thread
+extern "C" int tbk_unpack_mask_host(const uint8_t* bits, size_t nbits_bytes, uint8_t* out)
+{
+	if (!bits || !out) { tbk_set_error("tbk_unpack_mask_host: bad argument"); return TBK_ERR_INVALID; }
+	for (size_t i = 0; i < nbits_bytes; ++i) {
+		// byte j of (b * 0x8040201008040201 & 0x8080808080808080) >> 7 is bit (7 - j) of b
+		const unsigned long long x = ((((unsigned long long)bits[i] * 0x8040201008040201ULL) & 0x8080808080808080ULL) >> 7);
+		std::memcpy(out + 8 * i, &x, 8);
+	}
+	return TBK_OK;
+}
+
 extern "C" int tbk_sum_finalize(tbk_plan* p, const double* sum, const int32_t* nimg, const int32_t* used,
 	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, void* stream)
 {

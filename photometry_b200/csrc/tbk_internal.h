@@ -28,6 +28,7 @@ int tbk_launch_time_smooth(int H, int W, const float* bkg, int n, int w,
 int tbk_launch_sum_accumulate(const PlanDev& P, const float* cube, const float* bkg_smooth,
 	uint8_t* flags, const tbk_ffi_meta* meta, int n, float* flux_out,
 	double* sum, int32_t* nimg, int32_t* used, int* zero_flags, cudaStream_t st);
+int tbk_launch_pack_mask(const uint8_t* mask, size_t nbytes, uint8_t* bits, cudaStream_t st);
 int tbk_launch_sum_finalize(int H, int W, const double* sum, const int32_t* nimg, const int32_t* used,
 	int numfiles, double threshold, double* sumimage, uint8_t* pixels_used, cudaStream_t st);
 int tbk_launch_bkgshe_indicator(const float* images, const double* sum, int B, int H, int W, float* out, cudaStream_t st);

@@ -304,6 +304,39 @@ int tbk_launch_decode(const uint8_t* raw, int B, int naxis1, int naxis2, int row
 }
 
 // ---------------------------------------------------------------------------------------------
+// Mask bytes -> bits for the device-to-host copy of the end-to-end path (the link is the bottleneck there and the mask is
+// a fifth of the result bytes): bit (7 - j) of byte i = mask[8 i + j] != 0, the order of numpy.packbits.  One thread per
+// four output bytes (32 mask bytes, two 16-byte loads).
+__global__ void __launch_bounds__(256) k_pack_mask(const uint4* __restrict__ mask, size_t nwords, uint32_t* __restrict__ bits)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nwords) return;
+	const uint4 a = __ldg(mask + 2 * i), b = __ldg(mask + 2 * i + 1);
+	const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+	uint32_t out = 0u;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {       // output byte q <- mask bytes 8q .. 8q+7 = words 2q, 2q+1
+		uint32_t byte = 0u;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const uint32_t m = (w[2 * q + (j >> 2)] >> (8 * (j & 3))) & 0xFFu;
+			byte |= (m ? 1u : 0u) << (7 - j);
+		}
+		out |= byte << (8 * q);
+	}
+	bits[i] = out;
+}
+
+int tbk_launch_pack_mask(const uint8_t* mask, size_t nbytes, uint8_t* bits, cudaStream_t st)
+{
+	const size_t nwords = nbytes / 32;
+	if (nwords) k_pack_mask<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>((const uint4*)mask, nwords, (uint32_t*)bits);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { tbk_set_error("k_pack_mask: %s", cudaGetErrorString(e)); return TBK_ERR_CUDA; }
+	return TBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stamp gather (consumer side, photometry/BasePhotometry.py:720-751 _load_cube): for a target's stamp
 // (rows r0..r1, columns c0..c1 of the CCD) build cube[r][c][k] = stack[k][r0 + r][c0 + c] -- the (rows, cols, times)
 // array every photometry method works on.  Reads run along the columns of a frame, writes along time, so 32 x 32

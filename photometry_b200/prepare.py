@@ -158,53 +158,93 @@ def prepare_stack(fitter, cube, meta, time_smooth=3, extra_mask=None, chunk=8, k
 	return SectorResult(bkg_us, bkg, flags, images, sumimage, pixels_used, nimg, used, status_np, numfiles)
 
 
-def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3, extra_mask=None):
+def fit_stack_host(fitter, host_cube, meta, out_bkg, out_mask, chunk=16, nbuf=3, extra_mask=None, pack_mask=True, unpack_threads=6):
 	"""
 	End-to-end ``fit_background`` over a HOST-resident stack (the pool loop of prepare.py:291 with the
 	FFIs already decoded): pinned host cube -> device -> fit -> pinned host results, pipelined over
 	``nbuf`` device staging buffers and three streams (H2D, compute, D2H).
 
 	host_cube  float32 pinned CPU tensor [n, H, W];  out_bkg float32 / out_mask uint8 pinned CPU tensors
+	pack_mask  the device-to-host link bounds this path (21 MB out against 16.8 MB in per FFI) and the mask is a fifth of the
+	           result bytes: it crosses the link as bits (``tbk_pack_mask``) and a few host threads expand it into ``out_mask``
+	           (``tbk_unpack_mask_host``) while the next chunks are in flight.  The arrays the caller gets are the same.
 	Returns the number of bytes copied (h2d, d2h).  Raises ``ValueError`` (like the reference) when a frame has no usable mesh.
 	"""
-	from ._lib import STATUS_DTYPE
+	import ctypes as C
+	from concurrent.futures import ThreadPoolExecutor
+	from ._lib import STATUS_DTYPE, check
 	n, H, W = host_cube.shape
 	dev = fitter.device
 	ssz = STATUS_DTYPE.itemsize
 	status = torch.empty(n * ssz, dtype=torch.uint8, device=dev)
 	meta_d = fitter.meta_to_device(np.ascontiguousarray(meta))
 	isz = meta.dtype.itemsize
+	pack_mask = bool(pack_mask) and (H * W) % 32 == 0
 	s_in, s_c, s_out = (torch.cuda.Stream(dev) for _ in range(3))
 	ins = [torch.empty((chunk, H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
 	bks = [torch.empty((chunk, H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
 	mks = [torch.empty((chunk, H, W), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+	nbits = H * W // 8
+	if pack_mask:
+		bits_d = [torch.empty((chunk, nbits), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+		bits_h = [torch.empty((chunk, nbits), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+		pool = ThreadPoolExecutor(max_workers=max(1, int(unpack_threads)))
+		pending = [[] for _ in range(nbuf)]     # unpack jobs still reading bits_h[k]
+		out_ptr = out_mask.data_ptr()
+		lib = fitter.lib
+
+		def unpack(k, j, frame, ev):
+			ev.synchronize()                      # the chunk's bits have landed in bits_h[k]
+			check(lib.tbk_unpack_mask_host(C.c_void_p(bits_h[k].data_ptr() + j * nbits), nbits,
+				C.c_void_p(out_ptr + frame * H * W)), 'tbk_unpack_mask_host')
 	ev_in = [torch.cuda.Event() for _ in range(nbuf)]
 	ev_c = [torch.cuda.Event() for _ in range(nbuf)]
 	ev_out = [torch.cuda.Event() for _ in range(nbuf)]
 	cur = torch.cuda.current_stream(dev)
 	for s in (s_in, s_c, s_out):
 		s.wait_stream(cur)
-	for idx, a in enumerate(range(0, n, chunk)):
-		b = min(a + chunk, n)
-		m = b - a
-		k = idx % nbuf
-		if idx >= nbuf:
-			s_in.wait_event(ev_c[k])     # staging input free once its fit has run
-			s_c.wait_event(ev_out[k])    # result buffers free once copied out
-		with torch.cuda.stream(s_in):
-			ins[k][:m].copy_(host_cube[a:b], non_blocking=True)
-			ev_in[k].record(s_in)
-		s_c.wait_event(ev_in[k])
-		with torch.cuda.stream(s_c):
-			fitter.fit(ins[k][:m], meta_d[a * isz:b * isz], None if extra_mask is None else extra_mask[a:b].to(dev, non_blocking=True),
-				bkg_out=bks[k][:m], mask_out=mks[k][:m], status_out=status[a * ssz:b * ssz])
-			ev_c[k].record(s_c)
-		s_out.wait_event(ev_c[k])
-		with torch.cuda.stream(s_out):
-			out_bkg[a:b].copy_(bks[k][:m], non_blocking=True)
-			out_mask[a:b].copy_(mks[k][:m], non_blocking=True)
-			ev_out[k].record(s_out)
-	for s in (s_in, s_c, s_out):
-		cur.wait_stream(s)
-	check_status(status.cpu().numpy().view(STATUS_DTYPE))   # synchronises: the results are complete on return
-	return n * H * W * 4, n * H * W * 5
+	try:
+		for idx, a in enumerate(range(0, n, chunk)):
+			b = min(a + chunk, n)
+			m = b - a
+			k = idx % nbuf
+			if idx >= nbuf:
+				s_in.wait_event(ev_c[k])     # staging input free once its fit has run
+				s_c.wait_event(ev_out[k])    # result buffers free once copied out
+			with torch.cuda.stream(s_in):
+				ins[k][:m].copy_(host_cube[a:b], non_blocking=True)
+				ev_in[k].record(s_in)
+			s_c.wait_event(ev_in[k])
+			with torch.cuda.stream(s_c):
+				fitter.fit(ins[k][:m], meta_d[a * isz:b * isz], None if extra_mask is None else extra_mask[a:b].to(dev, non_blocking=True),
+					bkg_out=bks[k][:m], mask_out=mks[k][:m], status_out=status[a * ssz:b * ssz])
+				if pack_mask:
+					check(fitter.lib.tbk_pack_mask(C.c_void_p(mks[k].data_ptr()), m * H * W, C.c_void_p(bits_d[k].data_ptr()),
+						C.c_void_p(s_c.cuda_stream)), 'tbk_pack_mask')
+				ev_c[k].record(s_c)
+			s_out.wait_event(ev_c[k])
+			if pack_mask:
+				for f in pending[k]:
+					f.result()               # the previous chunk that used bits_h[k] has been expanded
+			with torch.cuda.stream(s_out):
+				out_bkg[a:b].copy_(bks[k][:m], non_blocking=True)
+				if pack_mask:
+					bits_h[k][:m].copy_(bits_d[k][:m], non_blocking=True)
+				else:
+					out_mask[a:b].copy_(mks[k][:m], non_blocking=True)
+				ev_out[k].record(s_out)
+			if pack_mask:
+				ev = torch.cuda.Event()
+				ev.record(s_out)
+				pending[k] = [pool.submit(unpack, k, j, a + j, ev) for j in range(m)]
+		for s in (s_in, s_c, s_out):
+			cur.wait_stream(s)
+		check_status(status.cpu().numpy().view(STATUS_DTYPE))   # synchronises: the device results are complete
+		if pack_mask:
+			for fl in pending:
+				for f in fl:
+					f.result()
+	finally:
+		if pack_mask:
+			pool.shutdown(wait=True)
+	return n * H * W * 4, n * H * W * 4 + (n * nbits if pack_mask else n * H * W)

@@ -356,9 +356,29 @@ def test_fit_stack_streams_match_single_launch():
 	assert torch.allclose(b0, b1, rtol=1e-6, atol=0)
 	# and through host buffers (the end-to-end path)
 	hb = torch.empty((n, H, W), dtype=torch.float32).pin_memory(); hm = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
-	pb.fit_stack_host(fit, torch.from_numpy(imgs).pin_memory(), meta, hb, hm, chunk=4)
-	torch.cuda.synchronize()
-	assert torch.equal(hm, m0.cpu()) and torch.allclose(hb, b0.cpu(), rtol=1e-6, atol=0)
+	for pack in (True, False):   # mask sent as bits and expanded by host threads / sent as bytes
+		hb.zero_(); hm.fill_(7)
+		h2d, d2h = pb.fit_stack_host(fit, torch.from_numpy(imgs).pin_memory(), meta, hb, hm, chunk=4, pack_mask=pack)
+		torch.cuda.synchronize()
+		assert torch.equal(hm, m0.cpu()) and torch.allclose(hb, b0.cpu(), rtol=1e-6, atol=0)
+		assert h2d == n * H * W * 4 and d2h == n * H * W * 4 + (n * H * W // 8 if pack else n * H * W)
+
+
+def test_mask_pack_unpack_round_trip():
+	"""tbk_pack_mask (device) / tbk_unpack_mask_host: the order of numpy.packbits, any non-zero byte counts as set."""
+	import ctypes as C
+	from photometry_b200 import _lib
+	lib = _lib.load()
+	rng = np.random.default_rng(8)
+	m = (rng.uniform(size=64 * 4096) < 0.3).astype('uint8') * rng.integers(1, 255, 64 * 4096).astype('uint8')
+	md = torch.from_numpy(m).cuda()
+	bits = torch.empty(m.size // 8, dtype=torch.uint8, device='cuda')
+	_lib.check(lib.tbk_pack_mask(C.c_void_p(md.data_ptr()), m.size, C.c_void_p(bits.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'tbk_pack_mask')
+	got = bits.cpu().numpy()
+	np.testing.assert_array_equal(got, np.packbits(m != 0))
+	out = np.empty(m.size, dtype='uint8')
+	_lib.check(lib.tbk_unpack_mask_host(got.ctypes.data_as(C.c_void_p), got.size, out.ctypes.data_as(C.c_void_p)), 'tbk_unpack_mask_host')
+	np.testing.assert_array_equal(out, (m != 0).astype('uint8'))
 
 
 # ---- edge cases: shapes, degenerate rings, ties, heavy masking -----------------------------------
