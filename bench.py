@@ -399,7 +399,7 @@ def run_b200(args):
 	host_bkg = torch.empty((ne, H, W), dtype=torch.float32).pin_memory()
 	host_mask = torch.empty((ne, H, W), dtype=torch.uint8).pin_memory()
 	def e2e_step():
-		return pb.fit_stack_host(fit, host_in, meta[:ne], host_bkg, host_mask, chunk=args.e2e_chunk)
+		return pb.fit_stack_host(fit, host_in, meta[:ne], host_bkg, host_mask, chunk=args.e2e_chunk, pack_mask=os.environ.get('TBK_E2E_PACK', '1') != '0')
 	e2e_step()
 	barrier()
 	esteps = max(1, min(args.steps, 3))
@@ -457,12 +457,19 @@ def run_b200(args):
 		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 		pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, nstreams=args.streams)
 		barrier()
-		ptm = {}
-		g0.record()
-		res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, timings=ptm, nstreams=args.streams)
-		g1.record()
-		barrier()
-		pms = g0.elapsed_time(g1)
+		# three timed calls, the median is reported: a call that has to grow the allocator's pool pays ~10 ms of cudaMalloc
+		runs = []
+		for _ in range(3):
+			res = None
+			ptm = {}
+			barrier()
+			g0.record()
+			res = pb.prepare_stack(fit, cube[:np_], meta[:np_], time_smooth=3, chunk=chunk, keep_images=True, timings=ptm, nstreams=args.streams)
+			g1.record()
+			barrier()
+			runs.append((g0.elapsed_time(g1), ptm))
+		runs.sort(key=lambda r: r[0])
+		pms, ptm = runs[1]
 		if world > 1:
 			t = torch.tensor([pms], dtype=torch.float64, device=dev)
 			dist.all_reduce(t, op=dist.ReduceOp.MAX)
