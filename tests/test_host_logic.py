@@ -133,3 +133,19 @@ def test_abi_rejects_bad_arguments_without_touching_the_gpu():
 	assert lib.tbk_debug_log10(null, one, 4, null) == -1
 	assert lib.tbk_debug_fetch(null, one, 1, 0, 0, null, null) == -1
 	assert b'tbk_debug_fetch' in lib.tbk_last_error()
+
+
+def test_host_mask_unpack_matches_numpy():
+	"""tbk_unpack_mask_host (the host half of the bit-packed mask transport) is numpy.unpackbits; no GPU involved."""
+	import ctypes as C
+	from photometry_b200 import _lib
+	lib = _lib.load()
+	rng = np.random.default_rng(3)
+	for nbytes in (1, 7, 64, 4096 * 3 + 5):
+		bits = rng.integers(0, 256, nbytes).astype('uint8')
+		out = np.full(nbytes * 8 + 8, 9, dtype='uint8')
+		rc = lib.tbk_unpack_mask_host(bits.ctypes.data_as(C.c_void_p), nbytes, out.ctypes.data_as(C.c_void_p))
+		assert rc == 0
+		np.testing.assert_array_equal(out[:nbytes * 8], np.unpackbits(bits))
+		assert (out[nbytes * 8:] == 9).all()   # nothing written past the end
+	assert lib.tbk_unpack_mask_host(None, 8, None) != 0
