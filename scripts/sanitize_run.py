@@ -26,3 +26,10 @@ imk = ImageMovementKernel(res.images[0])
 kern = imk.calc_kernels(res.images[:3], number_of_iterations=20)
 torch.cuda.synchronize()
 print('ok2', int(fitm.status_to_numpy(st)[0]['n_excluded'][0]), int(sm.sum()), kern.shape)
+# host-resident stack: pinned copies, bit-packed mask transport, host-side expansion; long time-smoothing windows
+hb = torch.empty((n, H, W), dtype=torch.float32).pin_memory(); hm = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
+pb.fit_stack_host(fit, torch.from_numpy(imgs).pin_memory(), pb.meta_from_headers(case['headers'][:4]), hb, hm, chunk=2)
+for w in (4, 13):
+	fit.time_smooth(res.backgrounds, w)
+torch.cuda.synchronize()
+print('ok3', int(hm.sum()))
